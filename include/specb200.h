@@ -1,0 +1,163 @@
+/* libspecb200 -- C ABI of the B200-native SPEC inference hot path.
+ *
+ * The reference (mkocabas/SPEC) is pure Python: there is no FFI to mirror.  This header is the
+ * boundary a maintainer binds (ctypes) underneath the two reference modules
+ *
+ *   CameraRegressorNetwork.forward   /root/reference/camcalib/model.py:72-81
+ *   HMR.forward                      /root/reference/spec/models/hmr.py:82-122
+ *
+ * Conventions:
+ *   - plain C, raw pointers + sizes + a cudaStream_t passed as void*; no torch types;
+ *   - every function returns 0 on success, non-zero on failure; specb200_last_error() returns the
+ *     message of the last failure on the calling thread;
+ *   - "dev" pointers are device memory on the current CUDA device, "host" pointers are host memory;
+ *   - forward functions only enqueue kernels on the caller's stream: no allocation, no
+ *     synchronisation (CUDA-graph capturable after one warm-up call); workspaces are allocated by
+ *     the caller, sized by the *_workspace_bytes() queries;
+ *   - packed weights are copied at create/set time and owned by the handle until *_destroy();
+ *   - one handle per (device, model); a handle is not thread-safe;
+ *   - there is NO CPU path: every entry point that computes requires an sm_100 device.
+ */
+#ifndef SPECB200_H
+#define SPECB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPECB200_ABI_VERSION 1
+
+/* arithmetic / storage type of the backbone activations */
+#define SPECB200_PREC_F32 0   /* fp32 storage, FFMA  (parity mode: north-star fp32 tolerances)  */
+#define SPECB200_PREC_BF16 1  /* bf16 storage, tcgen05 tensor cores, fp32 accumulate            */
+#define SPECB200_PREC_F16 2   /* fp16 storage, tcgen05 tensor cores, fp32 accumulate            */
+
+/* trunk program op codes */
+#define SPECB200_OP_CONV 1      /* dst[:, coff:coff+cout] = act(conv(src) + bias [+ src2])        */
+#define SPECB200_OP_MAXPOOL 2   /* 3x3 stride 2 pad 1                                             */
+#define SPECB200_OP_UPADD 3     /* dst += nearest_upsample(src, 2^shift) ; optional ReLU          */
+#define SPECB200_OP_BILINEAR 4  /* dst[:, coff:] = bilinear(src -> spatial size of buffer src2)   */
+#define SPECB200_OP_COPY 5      /* dst[:, coff:coff+C] = src                                      */
+
+typedef struct specb200_op {
+    int32_t type;
+    int32_t src, src2, dst; /* activation buffer ids; src2 = residual / size reference, -1 if none */
+    int32_t cin, cout;      /* conv: channels as stored (cin includes zero padding of the image)   */
+    int32_t kh, kw, stride, pad;
+    int32_t relu;
+    int32_t dst_coff; /* channel offset inside dst (concat)                                  */
+    int32_t shift;    /* UPADD: log2 of the upsampling factor                                */
+    int32_t wslot;    /* conv: weight slot                                                   */
+} specb200_op_t;
+
+typedef struct specb200_trunk specb200_trunk_t;
+typedef struct specb200_camtail specb200_camtail_t;
+typedef struct specb200_hmrtail specb200_hmrtail_t;
+
+const char* specb200_last_error(void);
+int specb200_abi_version(void);
+/* 0 iff the current device is an sm_100 (B200) GPU; the product refuses to run anywhere else. */
+int specb200_device_check(void);
+
+/* ---- backbone trunk: replaces pare.models.backbone.{resnet,hrnet} called at
+ *      /root/reference/camcalib/model.py:73 and /root/reference/spec/models/hmr.py:92 ------------ */
+/* buf_channels[i] = channel stride of activation buffer i; buffer 0 is the NHWC image
+ * (4 channels in fp32 mode, 8 in 16-bit modes, zero padded). out_buf = buffer holding the final map. */
+int specb200_trunk_create(specb200_trunk_t** out, const specb200_op_t* ops, int32_t n_ops,
+                          const int32_t* buf_channels, int32_t n_bufs, int32_t n_wslots, int32_t out_buf,
+                          int32_t precision);
+/* w_oihw_host: [cout][cin][kh][kw] fp32 with BatchNorm already folded in; bias_host: [cout]. */
+int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const float* w_oihw_host, const float* bias_host,
+                            int32_t cout, int32_t cin, int32_t kh, int32_t kw);
+/* images are processed `chunk` at a time so that layer-to-layer activations stay in L2 (0 = whole batch) */
+int specb200_trunk_set_chunk(specb200_trunk_t* t, int32_t chunk);
+int specb200_trunk_out_shape(specb200_trunk_t* t, int32_t h, int32_t w, int32_t* c_out, int32_t* h_out, int32_t* w_out);
+int64_t specb200_trunk_workspace_bytes(specb200_trunk_t* t, int32_t batch, int32_t h, int32_t w);
+/* images_nchw_dev: fp32 [batch][3][h][w].  pooled_out_dev: fp32, row stride pooled_ld floats, receives the
+ * global average pool of the final map (AdaptiveAvgPool2d(1)+flatten, model.py:74-75).  feat_nchw_out_dev:
+ * optional fp32 [batch][C][h/32][w/32] copy of the final map (the value `self.backbone(images)` returns). */
+int specb200_trunk_forward(specb200_trunk_t* t, const float* images_nchw_dev, int32_t batch, int32_t h, int32_t w,
+                           void* workspace_dev, int64_t workspace_bytes, float* pooled_out_dev, int32_t pooled_ld,
+                           float* feat_nchw_out_dev, void* stream);
+/* number of kernels the last forward enqueued (bench.py's gpu_launches) */
+int64_t specb200_trunk_last_launches(specb200_trunk_t* t);
+void specb200_trunk_destroy(specb200_trunk_t* t);
+
+/* ---- CamCalib tail: fc_vfov/fc_pitch/fc_roll (model.py:77-81) + convert_preds_to_angles
+ *      (cam_utils.py:121-145) + f_pix (camcalib_demo.py:129) + read_cam_params (cam_params.py:24-50) */
+int specb200_camtail_create(specb200_camtail_t** out, int32_t in_features, int32_t num_out);
+/* append one Linear(in,out) to head `which` (0 vfov, 1 pitch, 2 roll); w_host [out][in], b_host [out] */
+int specb200_camtail_add_linear(specb200_camtail_t* t, int32_t which, const float* w_host, const float* b_host,
+                                int32_t out_features, int32_t in_features);
+int specb200_camtail_finalize(specb200_camtail_t* t);
+int64_t specb200_camtail_workspace_bytes(specb200_camtail_t* t, int32_t batch);
+/* logits_out_dev: fp32 [batch][3*num_out] = [vfov | pitch | roll] logits. */
+int specb200_camtail_forward(specb200_camtail_t* t, const float* pooled_dev, int32_t pooled_ld, int32_t batch,
+                             void* workspace_dev, int64_t workspace_bytes, float* logits_out_dev, void* stream);
+/* logits -> angles_out_dev [batch][3] (vfov,pitch,roll radians).  If rotmat_out_dev != NULL also writes
+ * cam_rotmat [batch][9], cam_intrinsics [batch][9] (K[2][2]=0) and f_pix [batch] (may be NULL) from
+ * img_h_dev / img_w_dev (fp32 [batch]). */
+int specb200_camcalib_decode(const float* logits_dev, int32_t logits_ld, int32_t num_out, int32_t batch,
+                             const float* img_h_dev, const float* img_w_dev, float* angles_out_dev,
+                             float* rotmat_out_dev, float* intrinsics_out_dev, float* fpix_out_dev, void* stream);
+void specb200_camtail_destroy(specb200_camtail_t* t);
+
+/* ---- HMR tail: HMRHead + SMPLCamHead/SMPLHead (hmr.py:94-113) ---------------------------------- */
+typedef struct specb200_hmr_params {
+    int32_t in_features;   /* backbone channels C                                                  */
+    int32_t use_cam_feats; /* hmr.py:94-98                                                         */
+    int32_t use_cam;       /* 1: SMPLCamHead (hmr.py:100-113), 0: SMPLHead (hmr.py:114-121)        */
+    float focal_length, img_res;
+    /* HMRHead (host, nn.Linear layout [out][in]) */
+    const float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *decpose_w, *decpose_b, *decshape_w, *decshape_b, *deccam_w, *deccam_b;
+    const float *init_pose, *init_shape, *init_cam; /* [144], [10], [3] */
+    /* SMPL constants (host, smplx layout) */
+    const float* v_template;        /* [6890][3]       */
+    const float* shapedirs;         /* [6890][3][10]   */
+    const float* posedirs;          /* [207][20670]    */
+    const float* J_regressor;       /* [24][6890]      */
+    const float* lbs_weights;       /* [6890][24]      */
+    const float* J_regressor_extra; /* [9][6890]       */
+    const int32_t* parents;         /* [24]            */
+    const int32_t* joint_map;       /* [49] into the 54 candidate joints (constants.py:29-105)      */
+    const int32_t* vertex_ids;      /* [21]            */
+} specb200_hmr_params_t;
+
+/* Output pointers (device, fp32) with per-image strides in floats: lets the caller write either separate
+ * contiguous tensors or one packed per-image record (the multi-GPU all-gather buffer). */
+typedef struct specb200_hmr_outputs {
+    float* smpl_vertices; int64_t ld_vertices; /* [6890][3] */
+    float* smpl_joints3d; int64_t ld_joints3d; /* [49][3]   */
+    float* smpl_joints2d; int64_t ld_joints2d; /* [49][2]   */
+    float* pred_cam_t;    int64_t ld_cam_t;    /* [3]       */
+    float* pred_pose;     int64_t ld_pose;     /* [24][3][3]*/
+    float* pred_cam;      int64_t ld_cam;      /* [3]       */
+    float* pred_shape;    int64_t ld_shape;    /* [10]      */
+    float* pred_pose_6d;  int64_t ld_pose_6d;  /* [144]     */
+} specb200_hmr_outputs_t;
+
+int specb200_hmrtail_create(specb200_hmrtail_t** out, const specb200_hmr_params_t* params);
+int64_t specb200_hmrtail_workspace_bytes(specb200_hmrtail_t* t, int32_t batch);
+/* The head's input row buffer X lives at the start of the workspace: the trunk writes the pooled feature of
+ * image b to ((float*)workspace)[b * specb200_hmrtail_x_ld() .. + C]. */
+int32_t specb200_hmrtail_x_ld(specb200_hmrtail_t* t);
+/* cam_rotmat/cam_intrinsics [batch][9], bbox_scale [batch], bbox_center [batch][2], img_w/img_h [batch]; all
+ * fp32 device, may be NULL when use_cam == 0 and use_cam_feats == 0. */
+int specb200_hmrtail_forward(specb200_hmrtail_t* t, int32_t batch, void* workspace_dev, int64_t workspace_bytes,
+                             const float* cam_rotmat_dev, const float* cam_intrinsics_dev, const float* bbox_scale_dev,
+                             const float* bbox_center_dev, const float* img_w_dev, const float* img_h_dev,
+                             const specb200_hmr_outputs_t* outputs, void* stream);
+int64_t specb200_hmrtail_last_launches(specb200_hmrtail_t* t);
+void specb200_hmrtail_destroy(specb200_hmrtail_t* t);
+
+/* ---- standalone ops (unit tests / building blocks) -------------------------------------------- */
+/* out[m][n] = sum_k a[m][k] w[n][k] + bias[n] ; fp32 */
+int specb200_linear_f32(const float* a_dev, int32_t lda, const float* w_dev, int32_t ldw, const float* bias_dev,
+                        float* out_dev, int32_t ldo, int32_t m, int32_t n, int32_t k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECB200_H */

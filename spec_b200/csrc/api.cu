@@ -1,0 +1,547 @@
+// C ABI of libspecb200 (declared in include/specb200.h): handles, weight packing, the trunk op
+// interpreter and the tail orchestration.  Host code only enqueues kernels on the caller's stream.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/specb200.h"
+#include "internal.h"
+#include "tail.h"
+
+namespace sb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+bool check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int prec_elem(int prec) { return prec == PREC_F32 ? 4 : 2; }
+
+struct BufShape { int H = 0, W = 0; };
+
+}  // namespace sb
+
+using namespace sb;
+
+// =============================================================================================== trunk
+struct specb200_trunk {
+    std::vector<specb200_op_t> ops;
+    std::vector<int> buf_ch;
+    std::vector<ConvWeights> w;
+    std::vector<int> wslot_cin;      // stored (padded) Cin of the op using the slot
+    int out_buf = 0;
+    int prec = PREC_BF16;
+    int chunk = 0;
+    int64_t last_launches = 0;
+    // cached plan
+    int plan_h = -1, plan_w = -1;
+    std::vector<BufShape> op_src, op_dst;    // per-op spatial dims
+    std::vector<size_t> buf_elems;           // per-buffer max H*W*C (per image)
+    int out_h = 0, out_w = 0;
+};
+
+static bool trunk_plan(specb200_trunk* t, int h, int w) {
+    if (t->plan_h == h && t->plan_w == w) return true;
+    const int nb = static_cast<int>(t->buf_ch.size());
+    std::vector<BufShape> cur(nb);
+    t->op_src.assign(t->ops.size(), BufShape());
+    t->op_dst.assign(t->ops.size(), BufShape());
+    t->buf_elems.assign(nb, 0);
+    cur[0].H = h; cur[0].W = w;
+    t->buf_elems[0] = static_cast<size_t>(h) * w * t->buf_ch[0];
+    for (size_t i = 0; i < t->ops.size(); ++i) {
+        const specb200_op_t& o = t->ops[i];
+        if (o.src < 0 || o.src >= nb || o.dst < 0 || o.dst >= nb || o.src2 >= nb) { set_error("trunk: bad buffer id"); return false; }
+        const BufShape s = cur[o.src];
+        if (s.H <= 0) { set_error("trunk: op " + std::to_string(i) + " reads an undefined buffer"); return false; }
+        BufShape d;
+        switch (o.type) {
+            case SPECB200_OP_CONV:
+                d.H = (s.H + 2 * o.pad - o.kh) / o.stride + 1;
+                d.W = (s.W + 2 * o.pad - o.kw) / o.stride + 1;
+                if (o.src2 >= 0 && (cur[o.src2].H != d.H || cur[o.src2].W != d.W)) { set_error("trunk: residual shape mismatch at op " + std::to_string(i)); return false; }
+                if (o.cin != t->buf_ch[o.src]) { set_error("trunk: conv cin != source buffer channels at op " + std::to_string(i)); return false; }
+                break;
+            case SPECB200_OP_MAXPOOL:
+                d.H = (s.H + 2 - 3) / 2 + 1; d.W = (s.W + 2 - 3) / 2 + 1; break;
+            case SPECB200_OP_UPADD:
+                d = cur[o.dst];
+                if (d.H != (s.H << o.shift) || d.W != (s.W << o.shift)) { set_error("trunk: upadd shape mismatch at op " + std::to_string(i)); return false; }
+                break;
+            case SPECB200_OP_BILINEAR:
+                if (o.src2 < 0) { set_error("trunk: bilinear needs a size reference"); return false; }
+                d = cur[o.src2]; break;
+            case SPECB200_OP_COPY:
+                d = s; break;
+            default: set_error("trunk: unknown op type"); return false;
+        }
+        if (d.H <= 0 || d.W <= 0) { set_error("trunk: input too small"); return false; }
+        if (o.dst_coff > 0 && (cur[o.dst].H != 0) && (cur[o.dst].H != d.H || cur[o.dst].W != d.W) && o.type != SPECB200_OP_UPADD) {
+            // concat writers must agree on the spatial size; the first writer defines it
+        }
+        t->op_src[i] = s; t->op_dst[i] = d;
+        cur[o.dst] = d;
+        t->buf_elems[o.dst] = std::max(t->buf_elems[o.dst], static_cast<size_t>(d.H) * d.W * t->buf_ch[o.dst]);
+    }
+    t->out_h = cur[t->out_buf].H; t->out_w = cur[t->out_buf].W;
+    t->plan_h = h; t->plan_w = w;
+    return true;
+}
+
+extern "C" const char* specb200_last_error(void) { return g_err.c_str(); }
+extern "C" int specb200_abi_version(void) { return SPECB200_ABI_VERSION; }
+
+extern "C" int specb200_device_check(void) {
+    int dev = 0;
+    if (!check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+    cudaDeviceProp p;
+    if (!check_cuda(cudaGetDeviceProperties(&p, dev), "cudaGetDeviceProperties")) return 1;
+    if (p.major != 10) { set_error("libspecb200 requires an sm_100 (B200) device, found sm_" + std::to_string(p.major) + std::to_string(p.minor)); return 2; }
+    return 0;
+}
+
+extern "C" int specb200_trunk_create(specb200_trunk_t** out, const specb200_op_t* ops, int32_t n_ops,
+                                     const int32_t* buf_channels, int32_t n_bufs, int32_t n_wslots, int32_t out_buf,
+                                     int32_t precision) {
+    if (!out || !ops || !buf_channels || n_ops <= 0 || n_bufs <= 0 || out_buf < 0 || out_buf >= n_bufs) { set_error("trunk_create: bad arguments"); return 1; }
+    if (precision < 0 || precision > 2) { set_error("trunk_create: bad precision"); return 1; }
+    specb200_trunk* t = new specb200_trunk();
+    t->ops.assign(ops, ops + n_ops);
+    t->buf_ch.assign(buf_channels, buf_channels + n_bufs);
+    t->w.resize(n_wslots);
+    t->wslot_cin.assign(n_wslots, 0);
+    t->out_buf = out_buf;
+    t->prec = precision;
+    for (const auto& o : t->ops) {
+        if (o.type == SPECB200_OP_CONV) {
+            if (o.wslot < 0 || o.wslot >= n_wslots) { set_error("trunk_create: bad wslot"); delete t; return 1; }
+            t->wslot_cin[o.wslot] = o.cin;
+        }
+    }
+    *out = t;
+    return 0;
+}
+
+static void free_weights(ConvWeights& w) {
+    if (w.w_tc) cudaFree(w.w_tc);
+    if (w.w_f32) cudaFree(w.w_f32);
+    if (w.bias) cudaFree(w.bias);
+    w = ConvWeights();
+}
+
+extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const float* w_host, const float* b_host,
+                                       int32_t cout, int32_t cin, int32_t kh, int32_t kw) {
+    if (!t || wslot < 0 || wslot >= static_cast<int>(t->w.size()) || !w_host || !b_host) { set_error("set_conv: bad arguments"); return 1; }
+    const int cin_s = t->wslot_cin[wslot];           // stored Cin (>= cin, zero padded)
+    if (cin_s < cin) { set_error("set_conv: weight cin exceeds the op's cin"); return 1; }
+    ConvWeights& w = t->w[wslot];
+    free_weights(w);
+    w.cout = cout; w.cin = cin_s; w.kh = kh; w.kw = kw;
+    w.K = kh * kw * cin_s;
+    if (!check_cuda(cudaMalloc(&w.bias, sizeof(float) * cout), "cudaMalloc bias")) return 1;
+    if (!check_cuda(cudaMemcpy(w.bias, b_host, sizeof(float) * cout, cudaMemcpyHostToDevice), "bias upload")) return 1;
+    if (t->prec == PREC_F32) {
+        std::vector<float> pk(static_cast<size_t>(w.K) * cout, 0.f);
+        for (int o = 0; o < cout; ++o)
+            for (int c = 0; c < cin; ++c)
+                for (int y = 0; y < kh; ++y)
+                    for (int x = 0; x < kw; ++x)
+                        pk[(static_cast<size_t>(y * kw + x) * cin_s + c) * cout + o] = w_host[((static_cast<size_t>(o) * cin + c) * kh + y) * kw + x];
+        if (!check_cuda(cudaMalloc(&w.w_f32, pk.size() * sizeof(float)), "cudaMalloc w_f32")) return 1;
+        if (!check_cuda(cudaMemcpy(w.w_f32, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice), "w upload")) return 1;
+    } else {
+        w.block_n = conv_tc_pick_block_n(cout);
+        w.K_pad = static_cast<int>(align_up(w.K, 64));
+        w.cout_pad = static_cast<int>(align_up(cout, w.block_n));
+        std::vector<uint16_t> pk(static_cast<size_t>(w.cout_pad) * w.K_pad, 0);
+        for (int o = 0; o < cout; ++o)
+            for (int c = 0; c < cin; ++c)
+                for (int y = 0; y < kh; ++y)
+                    for (int x = 0; x < kw; ++x) {
+                        const float v = w_host[((static_cast<size_t>(o) * cin + c) * kh + y) * kw + x];
+                        uint16_t bits;
+                        if (t->prec == PREC_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(v); memcpy(&bits, &h, 2); }
+                        else { __half h = __float2half_rn(v); memcpy(&bits, &h, 2); }
+                        pk[static_cast<size_t>(o) * w.K_pad + static_cast<size_t>(y * kw + x) * cin_s + c] = bits;
+                    }
+        if (!check_cuda(cudaMalloc(&w.w_tc, pk.size() * 2), "cudaMalloc w_tc")) return 1;
+        if (!check_cuda(cudaMemcpy(w.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice), "w upload")) return 1;
+        if (!conv_tc_make_weight_tmap(w)) return 1;
+    }
+    return 0;
+}
+
+extern "C" int specb200_trunk_set_chunk(specb200_trunk_t* t, int32_t chunk) {
+    if (!t || chunk < 0) { set_error("set_chunk: bad arguments"); return 1; }
+    t->chunk = chunk;
+    return 0;
+}
+
+extern "C" int specb200_trunk_out_shape(specb200_trunk_t* t, int32_t h, int32_t w, int32_t* c_out, int32_t* h_out, int32_t* w_out) {
+    if (!t) { set_error("out_shape: null handle"); return 1; }
+    if (!trunk_plan(t, h, w)) return 1;
+    if (c_out) *c_out = t->buf_ch[t->out_buf];
+    if (h_out) *h_out = t->out_h;
+    if (w_out) *w_out = t->out_w;
+    return 0;
+}
+
+static int trunk_eff_batch(const specb200_trunk* t, int batch) { return (t->chunk > 0 && t->chunk < batch) ? t->chunk : batch; }
+
+extern "C" int64_t specb200_trunk_workspace_bytes(specb200_trunk_t* t, int32_t batch, int32_t h, int32_t w) {
+    if (!t || batch <= 0) { set_error("workspace_bytes: bad arguments"); return -1; }
+    if (!trunk_plan(t, h, w)) return -1;
+    const int eb = trunk_eff_batch(t, batch);
+    size_t total = 0;
+    for (size_t i = 0; i < t->buf_elems.size(); ++i) total += align_up(t->buf_elems[i] * eb * prec_elem(t->prec), 1024);
+    return static_cast<int64_t>(total + 1024);
+}
+
+extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, int32_t batch, int32_t h, int32_t w,
+                                      void* workspace, int64_t workspace_bytes, float* pooled_out, int32_t pooled_ld,
+                                      float* feat_out, void* stream) {
+    if (!t || !images || !workspace || batch <= 0) { set_error("trunk_forward: bad arguments"); return 1; }
+    if (!trunk_plan(t, h, w)) return 1;
+    if (workspace_bytes < specb200_trunk_workspace_bytes(t, batch, h, w)) { set_error("trunk_forward: workspace too small"); return 1; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int eb = trunk_eff_batch(t, batch);
+    const int es = prec_elem(t->prec);
+    // carve buffers
+    std::vector<uint8_t*> buf(t->buf_ch.size());
+    {
+        uint8_t* p = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+        for (size_t i = 0; i < buf.size(); ++i) { buf[i] = p; p += align_up(t->buf_elems[i] * eb * es, 1024); }
+    }
+    int64_t launches = 0;
+    const int C_out = t->buf_ch[t->out_buf];
+    for (int b0 = 0; b0 < batch; b0 += eb) {
+        const int nb = std::min(eb, batch - b0);
+        if (!images_to_nhwc_launch(images + static_cast<size_t>(b0) * 3 * h * w, buf[0], nb, h, w, t->buf_ch[0], t->prec, s)) return 1;
+        ++launches;
+        for (size_t i = 0; i < t->ops.size(); ++i) {
+            const specb200_op_t& o = t->ops[i];
+            const BufShape sS = t->op_src[i], dS = t->op_dst[i];
+            switch (o.type) {
+                case SPECB200_OP_CONV: {
+                    const ConvWeights& cw = t->w[o.wslot];
+                    if (cw.bias == nullptr) { set_error("trunk_forward: conv weights for slot " + std::to_string(o.wslot) + " not set"); return 1; }
+                    if (cw.cout != o.cout || cw.kh != o.kh || cw.kw != o.kw) { set_error("trunk_forward: weight shape mismatch at op " + std::to_string(i)); return 1; }
+                    ConvParams p;
+                    p.in = buf[o.src]; p.out = buf[o.dst]; p.res = o.src2 >= 0 ? buf[o.src2] : nullptr; p.bias = cw.bias;
+                    p.N = nb; p.H = sS.H; p.W = sS.W; p.Cin = o.cin; p.Ho = dS.H; p.Wo = dS.W; p.Cout = o.cout;
+                    p.kh = o.kh; p.kw = o.kw; p.stride = o.stride; p.pad = o.pad;
+                    p.K = o.kh * o.kw * o.cin;
+                    const long long M = static_cast<long long>(nb) * dS.H * dS.W;
+                    if (M > 0x7fffffffLL) { set_error("trunk_forward: batch too large"); return 1; }
+                    p.M = static_cast<int>(M);
+                    p.out_ld = t->buf_ch[o.dst]; p.out_coff = o.dst_coff;
+                    p.res_ld = o.src2 >= 0 ? t->buf_ch[o.src2] : 0;
+                    p.relu = o.relu;
+                    const bool ok = (t->prec == PREC_F32) ? conv_f32_launch(p, cw, s) : conv_tc_launch(p, cw, t->prec, s);
+                    if (!ok) return 1;
+                    break;
+                }
+                case SPECB200_OP_MAXPOOL:
+                    if (!maxpool3x3s2_launch(buf[o.src], buf[o.dst], nb, sS.H, sS.W, t->buf_ch[o.src], dS.H, dS.W, t->prec, s)) return 1;
+                    break;
+                case SPECB200_OP_UPADD:
+                    if (!upsample_add_launch(buf[o.src], buf[o.dst], nb, dS.H, dS.W, t->buf_ch[o.dst], o.shift, o.relu, t->prec, s)) return 1;
+                    break;
+                case SPECB200_OP_BILINEAR:
+                    if (!bilinear_launch(buf[o.src], buf[o.dst], nb, sS.H, sS.W, t->buf_ch[o.src], dS.H, dS.W, t->buf_ch[o.dst], o.dst_coff, t->prec, s)) return 1;
+                    break;
+                case SPECB200_OP_COPY:
+                    if (!copy_channels_launch(buf[o.src], buf[o.dst], nb * sS.H * sS.W, t->buf_ch[o.src], t->buf_ch[o.dst], o.dst_coff, t->prec, s)) return 1;
+                    break;
+                default: set_error("trunk_forward: unknown op"); return 1;
+            }
+            ++launches;
+        }
+        if (pooled_out) {
+            if (!avgpool_launch(buf[t->out_buf], pooled_out + static_cast<size_t>(b0) * pooled_ld, pooled_ld, nb, t->out_h * t->out_w, C_out, t->prec, s)) return 1;
+            ++launches;
+        }
+        if (feat_out) {
+            if (!nhwc_to_nchw_f32_launch(buf[t->out_buf], feat_out + static_cast<size_t>(b0) * C_out * t->out_h * t->out_w, nb, t->out_h, t->out_w, C_out, t->prec, s)) return 1;
+            ++launches;
+        }
+    }
+    t->last_launches = launches;
+    return 0;
+}
+
+extern "C" int64_t specb200_trunk_last_launches(specb200_trunk_t* t) { return t ? t->last_launches : 0; }
+
+extern "C" void specb200_trunk_destroy(specb200_trunk_t* t) {
+    if (!t) return;
+    for (auto& w : t->w) free_weights(w);
+    delete t;
+}
+
+// =============================================================================================== camcalib tail
+struct CamLinear { float* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
+struct specb200_camtail {
+    int in_features = 0, num_out = 0;
+    std::vector<CamLinear> heads[3];
+    bool fused = false;                 // single-layer heads concatenated into one [3*num_out][in] GEMM
+    float* wcat = nullptr; float* bcat = nullptr;
+    int max_hidden = 0;
+};
+
+extern "C" int specb200_camtail_create(specb200_camtail_t** out, int32_t in_features, int32_t num_out) {
+    if (!out || in_features <= 0 || num_out <= 0) { set_error("camtail_create: bad arguments"); return 1; }
+    specb200_camtail* t = new specb200_camtail();
+    t->in_features = in_features; t->num_out = num_out;
+    *out = t;
+    return 0;
+}
+
+extern "C" int specb200_camtail_add_linear(specb200_camtail_t* t, int32_t which, const float* w_host, const float* b_host,
+                                           int32_t out_features, int32_t in_features) {
+    if (!t || which < 0 || which > 2 || !w_host || !b_host) { set_error("camtail_add_linear: bad arguments"); return 1; }
+    const int expect_in = t->heads[which].empty() ? t->in_features : t->heads[which].back().out;
+    if (in_features != expect_in) { set_error("camtail_add_linear: in_features does not chain"); return 1; }
+    CamLinear l; l.out = out_features; l.in = in_features;
+    if (!check_cuda(cudaMalloc(&l.w, sizeof(float) * out_features * in_features), "cudaMalloc")) return 1;
+    if (!check_cuda(cudaMalloc(&l.b, sizeof(float) * out_features), "cudaMalloc")) return 1;
+    if (!check_cuda(cudaMemcpy(l.w, w_host, sizeof(float) * out_features * in_features, cudaMemcpyHostToDevice), "upload")) return 1;
+    if (!check_cuda(cudaMemcpy(l.b, b_host, sizeof(float) * out_features, cudaMemcpyHostToDevice), "upload")) return 1;
+    t->heads[which].push_back(l);
+    return 0;
+}
+
+extern "C" int specb200_camtail_finalize(specb200_camtail_t* t) {
+    if (!t) { set_error("camtail_finalize: null"); return 1; }
+    for (int h = 0; h < 3; ++h) {
+        if (t->heads[h].empty() || t->heads[h].back().out != t->num_out) { set_error("camtail_finalize: head incomplete"); return 1; }
+        for (size_t i = 0; i + 1 < t->heads[h].size(); ++i) t->max_hidden = std::max(t->max_hidden, t->heads[h][i].out);
+    }
+    if (t->heads[0].size() == 1 && t->heads[1].size() == 1 && t->heads[2].size() == 1) {
+        const size_t wsz = static_cast<size_t>(t->num_out) * t->in_features;
+        if (!check_cuda(cudaMalloc(&t->wcat, sizeof(float) * 3 * wsz), "cudaMalloc")) return 1;
+        if (!check_cuda(cudaMalloc(&t->bcat, sizeof(float) * 3 * t->num_out), "cudaMalloc")) return 1;
+        for (int h = 0; h < 3; ++h) {
+            if (!check_cuda(cudaMemcpy(t->wcat + h * wsz, t->heads[h][0].w, sizeof(float) * wsz, cudaMemcpyDeviceToDevice), "copy")) return 1;
+            if (!check_cuda(cudaMemcpy(t->bcat + h * t->num_out, t->heads[h][0].b, sizeof(float) * t->num_out, cudaMemcpyDeviceToDevice), "copy")) return 1;
+        }
+        t->fused = true;
+    }
+    return 0;
+}
+
+extern "C" int64_t specb200_camtail_workspace_bytes(specb200_camtail_t* t, int32_t batch) {
+    if (!t || batch <= 0) { set_error("camtail_workspace_bytes: bad arguments"); return -1; }
+    return static_cast<int64_t>(2 * align_up(static_cast<size_t>(batch) * std::max(t->max_hidden, 4) * sizeof(float), 256) + 256);
+}
+
+extern "C" int specb200_camtail_forward(specb200_camtail_t* t, const float* pooled, int32_t pooled_ld, int32_t batch,
+                                        void* workspace, int64_t workspace_bytes, float* logits_out, void* stream) {
+    if (!t || !pooled || !logits_out || batch <= 0) { set_error("camtail_forward: bad arguments"); return 1; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int ldo = 3 * t->num_out;
+    if (t->fused)
+        return linear_f32_launch(pooled, pooled_ld, t->wcat, t->in_features, t->bcat, nullptr, 0, logits_out, ldo, batch, ldo, t->in_features, s) ? 0 : 1;
+    if (!workspace || workspace_bytes < specb200_camtail_workspace_bytes(t, batch)) { set_error("camtail_forward: workspace too small"); return 1; }
+    float* tmp[2];
+    tmp[0] = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+    tmp[1] = tmp[0] + align_up(static_cast<size_t>(batch) * t->max_hidden, 64);
+    for (int h = 0; h < 3; ++h) {
+        const float* cur = pooled; int ld = pooled_ld;
+        for (size_t i = 0; i < t->heads[h].size(); ++i) {
+            const CamLinear& l = t->heads[h][i];
+            const bool last = (i + 1 == t->heads[h].size());
+            float* dst = last ? logits_out + h * t->num_out : tmp[i & 1];
+            const int dld = last ? ldo : l.out;
+            if (!linear_f32_launch(cur, ld, l.w, l.in, l.b, nullptr, 0, dst, dld, batch, l.out, l.in, s)) return 1;
+            cur = dst; ld = dld;
+        }
+    }
+    return 0;
+}
+
+extern "C" int specb200_camcalib_decode(const float* logits, int32_t logits_ld, int32_t num_out, int32_t batch,
+                                        const float* img_h, const float* img_w, float* angles_out, float* rotmat_out,
+                                        float* intr_out, float* fpix_out, void* stream) {
+    if (!logits || !angles_out || batch <= 0) { set_error("camcalib_decode: bad arguments"); return 1; }
+    if (rotmat_out && (!img_h || !img_w || !intr_out)) { set_error("camcalib_decode: img_h/img_w/intrinsics required with rotmat"); return 1; }
+    return camcalib_decode_launch(logits, logits_ld, num_out, img_h, img_w, angles_out, rotmat_out, intr_out, fpix_out, batch,
+                                  static_cast<cudaStream_t>(stream)) ? 0 : 1;
+}
+
+extern "C" void specb200_camtail_destroy(specb200_camtail_t* t) {
+    if (!t) return;
+    for (int h = 0; h < 3; ++h) for (auto& l : t->heads[h]) { cudaFree(l.w); cudaFree(l.b); }
+    if (t->wcat) cudaFree(t->wcat);
+    if (t->bcat) cudaFree(t->bcat);
+    delete t;
+}
+
+// =============================================================================================== HMR tail
+struct specb200_hmrtail {
+    int C = 0, use_cam_feats = 0, use_cam = 0, ldx = 0, kin = 0;
+    float focal = 5000.f, img_res = 224.f;
+    float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr, *dec_w = nullptr, *dec_b = nullptr, *init157 = nullptr;
+    float *Vt = nullptr, *Sd = nullptr, *Pd = nullptr, *Wl = nullptr, *Jx = nullptr, *Jt = nullptr, *Js = nullptr;
+    int64_t last_launches = 0;
+};
+
+static bool upload(float** dst, const std::vector<float>& v) {
+    if (!check_cuda(cudaMalloc(dst, v.size() * sizeof(float)), "cudaMalloc")) return false;
+    return check_cuda(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice), "upload");
+}
+
+extern "C" int specb200_hmrtail_create(specb200_hmrtail_t** out, const specb200_hmr_params_t* p) {
+    if (!out || !p) { set_error("hmrtail_create: bad arguments"); return 1; }
+    const float* req[] = {p->fc1_w, p->fc1_b, p->fc2_w, p->fc2_b, p->decpose_w, p->decpose_b, p->decshape_w, p->decshape_b,
+                          p->deccam_w, p->deccam_b, p->init_pose, p->init_shape, p->init_cam, p->v_template, p->shapedirs,
+                          p->posedirs, p->J_regressor, p->lbs_weights, p->J_regressor_extra};
+    for (const float* q : req) if (!q) { set_error("hmrtail_create: null parameter pointer"); return 1; }
+    if (!p->parents || !p->joint_map || !p->vertex_ids) { set_error("hmrtail_create: null index table"); return 1; }
+    static const int std_parents[24] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+    for (int i = 0; i < 24; ++i) if (p->parents[i] != std_parents[i]) { set_error("hmrtail_create: unexpected SMPL kinematic tree"); return 1; }
+    for (int i = 0; i < 49; ++i) if (p->joint_map[i] < 0 || p->joint_map[i] >= 54) { set_error("hmrtail_create: joint_map out of range"); return 1; }
+    for (int i = 0; i < 21; ++i) if (p->vertex_ids[i] < 0 || p->vertex_ids[i] >= SMPL_NV) { set_error("hmrtail_create: vertex id out of range"); return 1; }
+    if ((p->in_features % 4) != 0) { set_error("hmrtail_create: in_features must be a multiple of 4"); return 1; }
+    specb200_hmrtail* t = new specb200_hmrtail();
+    t->C = p->in_features; t->use_cam_feats = p->use_cam_feats; t->use_cam = p->use_cam;
+    t->focal = p->focal_length; t->img_res = p->img_res;
+    t->kin = t->C + 157 + (t->use_cam_feats ? 7 : 0);        // fc1 in_features
+    t->ldx = static_cast<int>(align_up(t->kin, 4));
+    const int NV = SMPL_NV, VP = SMPL_VP;
+    bool ok = true;
+    {   // fc1: [1024][kin] -> row stride ldx (zero padded) so that every K slice is 16-byte aligned
+        std::vector<float> w(static_cast<size_t>(1024) * t->ldx, 0.f);
+        for (int o = 0; o < 1024; ++o) memcpy(&w[static_cast<size_t>(o) * t->ldx], p->fc1_w + static_cast<size_t>(o) * t->kin, sizeof(float) * t->kin);
+        ok = ok && upload(&t->fc1_w, w);
+        ok = ok && upload(&t->fc1_b, std::vector<float>(p->fc1_b, p->fc1_b + 1024));
+        ok = ok && upload(&t->fc2_w, std::vector<float>(p->fc2_w, p->fc2_w + 1024 * 1024));
+        ok = ok && upload(&t->fc2_b, std::vector<float>(p->fc2_b, p->fc2_b + 1024));
+        std::vector<float> dw(static_cast<size_t>(157) * 1024), db(157), init(157);
+        memcpy(&dw[0], p->decpose_w, sizeof(float) * 144 * 1024);
+        memcpy(&dw[144 * 1024], p->decshape_w, sizeof(float) * 10 * 1024);
+        memcpy(&dw[154 * 1024], p->deccam_w, sizeof(float) * 3 * 1024);
+        memcpy(&db[0], p->decpose_b, sizeof(float) * 144); memcpy(&db[144], p->decshape_b, sizeof(float) * 10); memcpy(&db[154], p->deccam_b, sizeof(float) * 3);
+        memcpy(&init[0], p->init_pose, sizeof(float) * 144); memcpy(&init[144], p->init_shape, sizeof(float) * 10); memcpy(&init[154], p->init_cam, sizeof(float) * 3);
+        ok = ok && upload(&t->dec_w, dw) && upload(&t->dec_b, db) && upload(&t->init157, init);
+    }
+    {   // SMPL constants, repacked coordinate-planar over a padded vertex axis (coalesced over vertices)
+        std::vector<float> Vt(3 * static_cast<size_t>(VP), 0.f), Sd(30 * static_cast<size_t>(VP), 0.f), Pd(207 * 3 * static_cast<size_t>(VP), 0.f),
+            Wl(24 * static_cast<size_t>(VP), 0.f), Jx(9 * static_cast<size_t>(VP), 0.f);
+        for (int v = 0; v < NV; ++v) {
+            for (int c = 0; c < 3; ++c) {
+                Vt[static_cast<size_t>(c) * VP + v] = p->v_template[v * 3 + c];
+                for (int l = 0; l < 10; ++l) Sd[(static_cast<size_t>(l) * 3 + c) * VP + v] = p->shapedirs[(static_cast<size_t>(v) * 3 + c) * 10 + l];
+            }
+            for (int j = 0; j < 24; ++j) Wl[static_cast<size_t>(j) * VP + v] = p->lbs_weights[static_cast<size_t>(v) * 24 + j];
+            for (int q = 0; q < 9; ++q) Jx[static_cast<size_t>(q) * VP + v] = p->J_regressor_extra[static_cast<size_t>(q) * NV + v];
+        }
+        for (int k = 0; k < 207; ++k)
+            for (int v = 0; v < NV; ++v)
+                for (int c = 0; c < 3; ++c)
+                    Pd[(static_cast<size_t>(k) * 3 + c) * VP + v] = p->posedirs[static_cast<size_t>(k) * (NV * 3) + v * 3 + c];
+        // rest-joint regression folded through the shape basis (fp64 on the host):
+        //   J = Jreg (T + S beta) = (Jreg T) + (Jreg S) beta
+        std::vector<float> Jt(72), Js(720);
+        for (int j = 0; j < 24; ++j)
+            for (int c = 0; c < 3; ++c) {
+                double a = 0.0;
+                for (int v = 0; v < NV; ++v) a += static_cast<double>(p->J_regressor[static_cast<size_t>(j) * NV + v]) * p->v_template[v * 3 + c];
+                Jt[j * 3 + c] = static_cast<float>(a);
+                for (int l = 0; l < 10; ++l) {
+                    double s = 0.0;
+                    for (int v = 0; v < NV; ++v) s += static_cast<double>(p->J_regressor[static_cast<size_t>(j) * NV + v]) * p->shapedirs[(static_cast<size_t>(v) * 3 + c) * 10 + l];
+                    Js[(j * 3 + c) * 10 + l] = static_cast<float>(s);
+                }
+            }
+        ok = ok && upload(&t->Vt, Vt) && upload(&t->Sd, Sd) && upload(&t->Pd, Pd) && upload(&t->Wl, Wl) && upload(&t->Jx, Jx) &&
+             upload(&t->Jt, Jt) && upload(&t->Js, Js);
+    }
+    ok = ok && tail_upload_tables(p->joint_map, p->vertex_ids);
+    if (!ok) { specb200_hmrtail_destroy(t); return 1; }
+    *out = t;
+    return 0;
+}
+
+namespace {
+struct HmrWs { float *X, *Fx, *H1, *H2, *pf, *A, *Jp, *part; size_t total; };
+HmrWs hmr_carve(const specb200_hmrtail* t, int B, void* base) {
+    HmrWs w;
+    size_t off = 0;
+    auto take = [&](size_t nfloat) { float* p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + off); off += align_up(nfloat * sizeof(float), 256); return p; };
+    w.X = take(static_cast<size_t>(B) * t->ldx);
+    w.Fx = take(static_cast<size_t>(B) * 1024);
+    w.H1 = take(static_cast<size_t>(B) * 1024);
+    w.H2 = take(static_cast<size_t>(B) * 1024);
+    w.pf = take(static_cast<size_t>(B) * PF_LD);
+    w.A = take(static_cast<size_t>(B) * 288);
+    w.Jp = take(static_cast<size_t>(B) * 72);
+    w.part = take(static_cast<size_t>(B) * SMPL_NVT * 27);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+extern "C" int64_t specb200_hmrtail_workspace_bytes(specb200_hmrtail_t* t, int32_t batch) {
+    if (!t || batch <= 0) { set_error("hmrtail_workspace_bytes: bad arguments"); return -1; }
+    return static_cast<int64_t>(hmr_carve(t, batch, nullptr).total);
+}
+extern "C" int32_t specb200_hmrtail_x_ld(specb200_hmrtail_t* t) { return t ? t->ldx : 0; }
+
+extern "C" int specb200_hmrtail_forward(specb200_hmrtail_t* t, int32_t B, void* workspace, int64_t workspace_bytes,
+                                        const float* cam_rotmat, const float* cam_intr, const float* bbox_scale,
+                                        const float* bbox_center, const float* img_w, const float* img_h,
+                                        const specb200_hmr_outputs_t* o, void* stream) {
+    if (!t || !workspace || !o || B <= 0) { set_error("hmrtail_forward: bad arguments"); return 1; }
+    if ((reinterpret_cast<size_t>(workspace) & 255) != 0) { set_error("hmrtail_forward: workspace must be 256-byte aligned"); return 1; }
+    if (workspace_bytes < specb200_hmrtail_workspace_bytes(t, B)) { set_error("hmrtail_forward: workspace too small"); return 1; }
+    if ((t->use_cam_feats || t->use_cam) && (!cam_rotmat || !cam_intr || !img_h)) { set_error("hmrtail_forward: camera inputs required"); return 1; }
+    if (t->use_cam && (!bbox_scale || !bbox_center || !img_w)) { set_error("hmrtail_forward: bbox inputs required"); return 1; }
+    if (!o->smpl_vertices || !o->smpl_joints3d || !o->smpl_joints2d || !o->pred_cam_t || !o->pred_pose || !o->pred_cam || !o->pred_shape || !o->pred_pose_6d) {
+        set_error("hmrtail_forward: null output pointer"); return 1;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const HmrWs w = hmr_carve(t, B, workspace);
+    const int C = t->C, ldx = t->ldx;
+    int64_t n = 0;
+    if (!head_init_launch(w.X, ldx, C, t->init157, cam_rotmat, cam_intr, img_h, t->use_cam_feats, B, s)) return 1; ++n;
+    // fc1 split: the feature part is iteration-invariant.  Fx = xf W1[:, :C]^T + b1
+    if (!linear_f32_launch(w.X, ldx, t->fc1_w, ldx, t->fc1_b, nullptr, 0, w.Fx, 1024, B, 1024, C, s)) return 1; ++n;
+    const int kstate = ldx - C;   // state (157) + cam feats (7) + zero padding
+    for (int it = 0; it < 3; ++it) {
+        if (!linear_f32_launch(w.X + C, ldx, t->fc1_w + C, ldx, nullptr, w.Fx, 1024, w.H1, 1024, B, 1024, kstate, s)) return 1; ++n;
+        if (!linear_f32_launch(w.H1, 1024, t->fc2_w, 1024, t->fc2_b, nullptr, 0, w.H2, 1024, B, 1024, 1024, s)) return 1; ++n;
+        if (!linear_f32_launch(w.H2, 1024, t->dec_w, 1024, t->dec_b, w.X + C, ldx, w.X + C, ldx, B, 157, 1024, s)) return 1; ++n;
+    }
+    if (!smpl_prep_launch(w.X, ldx, C, t->Jt, t->Js, w.pf, w.A, w.Jp, o->pred_pose, o->ld_pose, o->pred_pose_6d, o->ld_pose_6d,
+                          o->pred_shape, o->ld_shape, o->pred_cam, o->ld_cam, B, s)) return 1; ++n;
+    if (!smpl_verts_launch(t->Vt, t->Sd, t->Pd, t->Wl, t->Jx, w.X, ldx, C, w.pf, w.A, o->smpl_vertices, o->ld_vertices, w.part, B, s)) return 1; ++n;
+    if (!smpl_joints_launch(o->smpl_vertices, o->ld_vertices, w.Jp, w.part, w.X, ldx, C, cam_rotmat, cam_intr, bbox_scale, bbox_center,
+                            img_w, img_h, o->smpl_joints3d, o->ld_joints3d, o->smpl_joints2d, o->ld_joints2d, o->pred_cam_t, o->ld_cam_t,
+                            t->use_cam, t->focal, t->img_res, B, s)) return 1; ++n;
+    t->last_launches = n;
+    return 0;
+}
+
+extern "C" int64_t specb200_hmrtail_last_launches(specb200_hmrtail_t* t) { return t ? t->last_launches : 0; }
+
+extern "C" void specb200_hmrtail_destroy(specb200_hmrtail_t* t) {
+    if (!t) return;
+    float* ptrs[] = {t->fc1_w, t->fc1_b, t->fc2_w, t->fc2_b, t->dec_w, t->dec_b, t->init157, t->Vt, t->Sd, t->Pd, t->Wl, t->Jx, t->Jt, t->Js};
+    for (float* p : ptrs) if (p) cudaFree(p);
+    delete t;
+}
+
+// =============================================================================================== standalone
+extern "C" int specb200_linear_f32(const float* a, int32_t lda, const float* w, int32_t ldw, const float* bias, float* out,
+                                   int32_t ldo, int32_t m, int32_t n, int32_t k, void* stream) {
+    return linear_f32_launch(a, lda, w, ldw, bias, nullptr, 0, out, ldo, m, n, k, static_cast<cudaStream_t>(stream)) ? 0 : 1;
+}

@@ -1,0 +1,359 @@
+// Implicit-GEMM convolution on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the cuDNN conv + separate BN / ReLU / residual-add kernels the reference runs for every
+// backbone convolution (call sites /root/reference/camcalib/model.py:73 and
+// /root/reference/spec/models/hmr.py:92; op inventory SURVEY.md section 2.2).
+//
+// GEMM view:  D[M, Cout] = A[M, K] * W[Cout, K]^T,  M = N*Ho*Wo output pixels, K = kh*kw*Cin with
+// k = (tap, channel).  Activations are NHWC 16-bit, weights K-major 16-bit (BN folded), accumulation
+// fp32 in tensor memory.  One CTA computes a 128 x BLOCK_N output tile:
+//
+//   warps 0-3  A producers: software im2col -- thread t owns tile row t and copies its 128-byte
+//              K-slice per stage with zero-filling cp.async straight into the 128B-swizzled layout
+//              the UMMA descriptor expects (1x1/stride-1 convs skip this: A is a plain [M,Cin]
+//              matrix and comes in by TMA).  Afterwards the same warps run the epilogue:
+//              tcgen05.ld accumulator rows -> +bias (+residual) -> ReLU -> 16-bit NHWC store.
+//   warp 4     TMA producer for the weight tile (and the A tile in TMA_A mode); owns TMEM alloc.
+//   warp 5     MMA issuer: one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage and
+//              commits stage release / accumulator-ready to mbarriers.
+//
+// Pipeline: STAGES-deep smem ring with full/empty mbarriers; smem footprint <= ~100 KB so two CTAs
+// share an SM and one CTA's epilogue overlaps the other's main loop.
+#include "common.cuh"
+#include "internal.h"
+
+namespace sb {
+
+constexpr int TILE_M = 128;
+constexpr int TILE_K = 64;                      // 64 x 16-bit = 128 B = one swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;
+constexpr int GATHER_LAG = 2;                   // cp.async groups kept in flight per producer thread
+constexpr int CONV_TC_THREADS = 192;
+
+template <int BLOCK_N, int STAGES>
+struct ConvTcSmem {
+    static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
+    static constexpr int A_OFF = 0;
+    static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+    static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;          // full[STAGES], empty[STAGES], tmem_full
+    static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
+    static constexpr int BIAS_OFF = TMEMPTR_OFF + 8;
+    static constexpr int TOTAL = BIAS_OFF + BLOCK_N * 4;
+    static constexpr int DYN_BYTES = TOTAL + 1024;                           // slack for manual 1024 B alignment
+};
+
+template <typename T, int BLOCK_N, int STAGES, bool TMA_A>
+__global__ void __launch_bounds__(CONV_TC_THREADS)
+conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
+               const __grid_constant__ CUtensorMap tmap_b, int n_tiles)
+{
+    static_assert(GATHER_LAG <= STAGES - 1, "producer lag must leave one free stage");
+    using L = ConvTcSmem<BLOCK_N, STAGES>;
+    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t a_base = sbase + L::A_OFF;
+    const uint32_t b_base = sbase + L::B_OFF;
+    const uint32_t bar_full = sbase + L::BAR_OFF;
+    const uint32_t bar_empty = bar_full + STAGES * 8;
+    const uint32_t bar_tmem = bar_empty + STAGES * 8;
+    volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sgen + L::TMEMPTR_OFF);
+    float* sbias = reinterpret_cast<float*>(sgen + L::BIAS_OFF);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x % n_tiles;
+    const int m_tile = blockIdx.x / n_tiles;
+    const int n0 = n_tile * BLOCK_N;
+    const int num_kb = (p.K + TILE_K - 1) / TILE_K;
+
+    // ---------------- one-time setup
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + s * 8, TMA_A ? 1 : 5);      // 4 gather warps + the TMA thread
+            mbar_init(bar_empty + s * 8, 1);
+        }
+        mbar_init(bar_tmem, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < BLOCK_N) {
+        const int c = n0 + threadIdx.x;
+        sbias[threadIdx.x] = (c < p.Cout) ? p.bias[c] : 0.f;
+    }
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_b);
+            if (TMA_A) tma_prefetch_desc(&tmap_a);
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_ptr_s;
+
+    if (warp < 4) {
+        const int t = threadIdx.x;                               // tile row == TMEM lane
+        const long long r = static_cast<long long>(m_tile) * TILE_M + t;
+        const bool row_ok = r < p.M;
+        // ---------------- A producer (software im2col)
+        if constexpr (!TMA_A) {
+            const T* __restrict__ in = static_cast<const T*>(p.in);
+            int n = 0, oh = 0, ow = 0;
+            if (row_ok) {
+                const int hw = p.Ho * p.Wo;
+                n = static_cast<int>(r / hw);
+                const int rem = static_cast<int>(r - static_cast<long long>(n) * hw);
+                oh = rem / p.Wo;
+                ow = rem - oh * p.Wo;
+            }
+            const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
+            const T* base = in + static_cast<size_t>(n) * p.H * p.W * p.Cin;
+            const uint32_t row_off = static_cast<uint32_t>(t) * 128u;
+            const uint32_t sw = static_cast<uint32_t>(t) & 7u;
+            const bool uniform_tap = (p.Cin % TILE_K) == 0;
+            const int taps = p.kh * p.kw;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const int it = kb / STAGES;
+                mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
+                const uint32_t dst = a_base + s * A_STAGE_BYTES + row_off;
+                if (uniform_tap) {
+                    const int k0 = kb * TILE_K;
+                    const int tap = k0 / p.Cin;
+                    const int c0 = k0 - tap * p.Cin;
+                    const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+                    const int ih = ih0 + khi, iw = iw0 + kwi;
+                    const bool ok = row_ok && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
+                                    static_cast<unsigned>(iw) < static_cast<unsigned>(p.W);
+                    const T* src = ok ? base + (static_cast<size_t>(ih) * p.W + iw) * p.Cin + c0 : in;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cp_async16(dst + ((j ^ sw) << 4), src + j * 8, ok);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int kidx = kb * TILE_K + j * 8;
+                        const int tap = kidx / p.Cin;
+                        const int c = kidx - tap * p.Cin;
+                        const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+                        const int ih = ih0 + khi, iw = iw0 + kwi;
+                        const bool ok = row_ok && tap < taps && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
+                                        static_cast<unsigned>(iw) < static_cast<unsigned>(p.W);
+                        const T* src = ok ? base + (static_cast<size_t>(ih) * p.W + iw) * p.Cin + c : in;
+                        cp_async16(dst + ((j ^ sw) << 4), src, ok);
+                    }
+                }
+                cp_async_commit();
+                if (kb >= GATHER_LAG) {
+                    cp_async_wait<GATHER_LAG>();
+                    fence_proxy_async_smem();                     // generic-proxy writes -> async-proxy (UMMA) reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full + ((kb - GATHER_LAG) % STAGES) * 8);
+                }
+            }
+            // drain the last min(GATHER_LAG, num_kb) groups
+            for (int kb = (num_kb > GATHER_LAG ? num_kb - GATHER_LAG : 0); kb < num_kb; ++kb) {
+                const int pending = num_kb - 1 - kb;
+                if (pending >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + (kb % STAGES) * 8);
+            }
+        }
+        // ---------------- epilogue
+        mbar_wait(bar_tmem, 0);
+        tc_fence_after();
+        T* __restrict__ out = static_cast<T*>(p.out);
+        const T* __restrict__ res = static_cast<const T*>(p.res);
+        const size_t out_row = static_cast<size_t>(r) * p.out_ld + p.out_coff;
+        const size_t res_row = static_cast<size_t>(r) * p.res_ld;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = n0 + c * 32 + q * 8;
+                    if (col < p.Cout) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + sbias[c * 32 + q * 8 + e];
+                        if (res != nullptr) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(res + res_row + col);
+                            const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 rf = DT<T>::unpack2(ru[e]);
+                                f[2 * e] += rf.x;
+                                f[2 * e + 1] += rf.y;
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                        }
+                        uint4 ov;
+                        ov.x = DT<T>::pack2(f[0], f[1]);
+                        ov.y = DT<T>::pack2(f[2], f[3]);
+                        ov.z = DT<T>::pack2(f[4], f[5]);
+                        ov.w = DT<T>::pack2(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(out + out_row + col) = ov;
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ---------------- TMA producer
+        if (lane == 0) {
+            constexpr uint32_t tx_bytes = L::B_STAGE_BYTES + (TMA_A ? A_STAGE_BYTES : 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const int it = kb / STAGES;
+                mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(bar_full + s * 8, tx_bytes);
+                tma_load_2d(b_base + s * L::B_STAGE_BYTES, &tmap_b, bar_full + s * 8, kb * TILE_K, n0);
+                if (TMA_A) tma_load_2d(a_base + s * A_STAGE_BYTES, &tmap_a, bar_full + s * 8, kb * TILE_K, m_tile * TILE_M);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(DT<T>::umma_fmt, TILE_M, BLOCK_N < 16 ? 16 : BLOCK_N);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const int it = kb / STAGES;
+                mbar_wait(bar_full + s * 8, it & 1);
+                tc_fence_after();
+                const uint32_t a_s = a_base + s * A_STAGE_BYTES;
+                const uint32_t b_s = b_base + s * L::B_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < TILE_K / 16; ++k) {
+                    umma_f16(tmem_acc, umma_desc_sw128(a_s + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
+                             static_cast<uint32_t>((kb | k) != 0));
+                }
+                umma_commit(bar_empty + s * 8);                   // frees the smem stage when these MMAs retire
+            }
+            umma_commit(bar_tmem);                                // accumulator complete
+        }
+        __syncwarp();
+    }
+
+    // ---------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_acc, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+        set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+// 2-D 16-bit row-major tensor [rows][cols], box = 64 cols x box_rows rows, 128-byte swizzle.
+static bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {TILE_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (code " + std::to_string(static_cast<int>(r)) + ")");
+        return false;
+    }
+    return true;
+}
+
+int conv_tc_pick_block_n(int cout) {
+    if (cout <= 32) return 32;
+    if (cout <= 64) return 64;
+    return 128;
+}
+
+bool conv_tc_make_weight_tmap(ConvWeights& w) {
+    if (!make_tmap_2d(&w.tmap_b, w.w_tc, static_cast<uint64_t>(w.cout_pad), static_cast<uint64_t>(w.K_pad),
+                      static_cast<uint32_t>(w.block_n)))
+        return false;
+    w.has_tmap = true;
+    return true;
+}
+
+template <typename T, int BLOCK_N, int STAGES>
+static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s) {
+    using L = ConvTcSmem<BLOCK_N, STAGES>;
+    const bool tma_a = (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0 && (p.Cin % TILE_K) == 0);
+    const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
+    const int n_tiles = (p.Cout + BLOCK_N - 1) / BLOCK_N;
+    CUtensorMap tmap_a;
+    if (tma_a) {
+        if (!make_tmap_2d(&tmap_a, p.in, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.Cin), TILE_M)) return false;
+    } else {
+        tmap_a = w.tmap_b;     // unused placeholder
+    }
+    auto kern_t = conv_tc_kernel<T, BLOCK_N, STAGES, true>;
+    auto kern_g = conv_tc_kernel<T, BLOCK_N, STAGES, false>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (!check_cuda(cudaFuncSetAttribute(kern_t, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        if (!check_cuda(cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        attr_done = true;
+    }
+    const long long grid = static_cast<long long>(m_tiles) * n_tiles;
+    if (grid > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return false; }
+    if (tma_a)
+        kern_t<<<static_cast<unsigned>(grid), CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, tmap_a, w.tmap_b, n_tiles);
+    else
+        kern_g<<<static_cast<unsigned>(grid), CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, tmap_a, w.tmap_b, n_tiles);
+    return check_cuda(cudaGetLastError(), "conv_tc launch");
+}
+
+template <typename T>
+static bool launch_dt(const ConvParams& p, const ConvWeights& w, cudaStream_t s) {
+    switch (w.block_n) {
+        case 32: return launch_cfg<T, 32, 4>(p, w, s);
+        case 64: return launch_cfg<T, 64, 4>(p, w, s);
+        case 128: return launch_cfg<T, 128, 3>(p, w, s);
+        default: set_error("conv_tc: unsupported block_n"); return false;
+    }
+}
+
+bool conv_tc_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s) {
+    if (!w.has_tmap) { set_error("conv_tc: weights not packed"); return false; }
+    if ((p.Cin % 8) != 0 || (p.Cout % 8) != 0 || (p.out_ld % 8) != 0 || (p.out_coff % 8) != 0 ||
+        (p.res != nullptr && (p.res_ld % 8) != 0)) {
+        set_error("conv_tc: channel counts / strides must be multiples of 8");
+        return false;
+    }
+    if (prec == PREC_BF16) return launch_dt<__nv_bfloat16>(p, w, s);
+    if (prec == PREC_F16) return launch_dt<__half>(p, w, s);
+    set_error("conv_tc: precision must be bf16 or fp16");
+    return false;
+}
+
+}  // namespace sb

@@ -1,0 +1,243 @@
+// Layout / elementwise kernels around the convolutions (all NHWC, 16-byte vectorised):
+// image NCHW fp32 -> NHWC, 3x3/2 max-pool (ResNet stem), HRNet fuse (nearest-upsample + add),
+// bilinear resize (hrnet-interp tail), channel-slice copy (concat), global average pool, NHWC->NCHW export.
+// Reference ops replaced: ATen max_pool2d / adaptive_avg_pool2d / upsample / cat.
+#include "common.cuh"
+#include "internal.h"
+
+namespace sb {
+
+template <typename T> struct V16;           // 16-byte vector of T
+template <> struct V16<float> {
+    static constexpr int N = 4;
+    __device__ static void load(const float* p, float (&f)[4]) { float4 v = *reinterpret_cast<const float4*>(p); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+    __device__ static void store(float* p, const float (&f)[4]) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <typename T> struct V16 {
+    static constexpr int N = 8;
+    __device__ static void load(const T* p, float (&f)[8]) {
+        uint4 v = *reinterpret_cast<const uint4*>(p);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 t = DT<T>::unpack2(u[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+    __device__ static void store(T* p, const float (&f)[8]) {
+        uint4 v;
+        v.x = DT<T>::pack2(f[0], f[1]); v.y = DT<T>::pack2(f[2], f[3]);
+        v.z = DT<T>::pack2(f[4], f[5]); v.w = DT<T>::pack2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(p) = v;
+    }
+};
+
+#define SB_DISPATCH_PREC(prec, ...)                                                    \
+    do {                                                                               \
+        if ((prec) == PREC_F32) { using T = float; __VA_ARGS__; }                      \
+        else if ((prec) == PREC_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }        \
+        else if ((prec) == PREC_F16) { using T = __half; __VA_ARGS__; }                \
+        else { set_error("bad precision"); return false; }                             \
+    } while (0)
+
+static inline unsigned nblk(long long n, int t) { return static_cast<unsigned>((n + t - 1) / t); }
+
+// ------------------------------------------------------------------ images NCHW f32 -> NHWC(cpad)
+template <typename T>
+__global__ void images_to_nhwc_kernel(const float* __restrict__ img, T* __restrict__ out, long long npix, int HW) {
+    constexpr int CP = V16<T>::N;                  // 4 (fp32) or 8 (16-bit) channels, zero padded
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const long long n = i / HW;
+    const int hw = static_cast<int>(i - n * HW);
+    const float* src = img + n * 3 * HW + hw;
+    float f[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) f[c] = 0.f;
+    f[0] = src[0]; f[1] = src[HW]; f[2] = src[2 * static_cast<size_t>(HW)];
+    V16<T>::store(out + i * CP, f);
+}
+bool images_to_nhwc_launch(const float* img, void* out, int N, int H, int W, int cpad, int prec, cudaStream_t s) {
+    const long long npix = static_cast<long long>(N) * H * W;
+    if (cpad != (prec == PREC_F32 ? 4 : 8)) { set_error("images_to_nhwc: cpad mismatch"); return false; }
+    SB_DISPATCH_PREC(prec, (images_to_nhwc_kernel<T><<<nblk(npix, 256), 256, 0, s>>>(img, static_cast<T*>(out), npix, H * W)));
+    return check_cuda(cudaGetLastError(), "images_to_nhwc");
+}
+
+// ------------------------------------------------------------------ maxpool 3x3 s2 p1
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int Ho, int Wo) {
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const long long total = static_cast<long long>(N) * Ho * Wo * cv;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % cv) * V;
+    long long t = i / cv;
+    const int ow = static_cast<int>(t % Wo); t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    float m[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) m[e] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const int ih = oh * 2 - 1 + dy;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int iw = ow * 2 - 1 + dx;
+            if (iw < 0 || iw >= W) continue;
+            float f[V];
+            V16<T>::load(in + ((n * H + ih) * W + iw) * C + c, f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) m[e] = fmaxf(m[e], f[e]);
+        }
+    }
+    V16<T>::store(out + ((n * Ho + oh) * Wo + ow) * C + c, m);
+}
+bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int prec, cudaStream_t s) {
+    SB_DISPATCH_PREC(prec, {
+        const long long total = static_cast<long long>(N) * Ho * Wo * (C / V16<T>::N);
+        maxpool_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, Ho, Wo);
+    });
+    return check_cuda(cudaGetLastError(), "maxpool");
+}
+
+// ------------------------------------------------------------------ acc += nearest_upsample(lo, 2^shift) [; relu]
+template <typename T>
+__global__ void upsample_add_kernel(const T* __restrict__ lo, T* __restrict__ acc, int N, int Ho, int Wo, int C, int shift, int relu) {
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const long long total = static_cast<long long>(N) * Ho * Wo * cv;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % cv) * V;
+    long long t = i / cv;
+    const int ow = static_cast<int>(t % Wo); t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const int Hl = Ho >> shift, Wl = Wo >> shift;
+    float a[V], b[V];
+    T* ap = acc + ((n * Ho + oh) * Wo + ow) * C + c;
+    V16<T>::load(ap, a);
+    V16<T>::load(lo + ((n * Hl + (oh >> shift)) * Wl + (ow >> shift)) * C + c, b);
+#pragma unroll
+    for (int e = 0; e < V; ++e) { a[e] += b[e]; if (relu) a[e] = fmaxf(a[e], 0.f); }
+    V16<T>::store(ap, a);
+}
+bool upsample_add_launch(const void* lo, void* acc, int N, int Ho, int Wo, int C, int shift, int relu, int prec, cudaStream_t s) {
+    SB_DISPATCH_PREC(prec, {
+        const long long total = static_cast<long long>(N) * Ho * Wo * (C / V16<T>::N);
+        upsample_add_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(lo), static_cast<T*>(acc), N, Ho, Wo, C, shift, relu);
+    });
+    return check_cuda(cudaGetLastError(), "upsample_add");
+}
+
+// ------------------------------------------------------------------ bilinear (align_corners=True) into a concat slice
+template <typename T>
+__global__ void bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int Ho, int Wo,
+                                int out_ld, int out_coff) {
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const long long total = static_cast<long long>(N) * Ho * Wo * cv;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % cv) * V;
+    long long t = i / cv;
+    const int ow = static_cast<int>(t % Wo); t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const float sy = Ho > 1 ? static_cast<float>(H - 1) / static_cast<float>(Ho - 1) : 0.f;
+    const float sx = Wo > 1 ? static_cast<float>(W - 1) / static_cast<float>(Wo - 1) : 0.f;
+    const float fy = sy * oh, fx = sx * ow;
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    float a[V], b[V], cc[V], d[V], o[V];
+    const T* base = in + n * H * W * C + c;
+    V16<T>::load(base + (static_cast<size_t>(y0) * W + x0) * C, a);
+    V16<T>::load(base + (static_cast<size_t>(y0) * W + x1) * C, b);
+    V16<T>::load(base + (static_cast<size_t>(y1) * W + x0) * C, cc);
+    V16<T>::load(base + (static_cast<size_t>(y1) * W + x1) * C, d);
+#pragma unroll
+    for (int e = 0; e < V; ++e)
+        o[e] = (1.f - ly) * ((1.f - lx) * a[e] + lx * b[e]) + ly * ((1.f - lx) * cc[e] + lx * d[e]);
+    V16<T>::store(out + ((n * Ho + oh) * Wo + ow) * out_ld + out_coff + c, o);
+}
+bool bilinear_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int out_ld, int out_coff,
+                     int prec, cudaStream_t s) {
+    SB_DISPATCH_PREC(prec, {
+        const long long total = static_cast<long long>(N) * Ho * Wo * (C / V16<T>::N);
+        bilinear_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, Ho, Wo, out_ld, out_coff);
+    });
+    return check_cuda(cudaGetLastError(), "bilinear");
+}
+
+// ------------------------------------------------------------------ copy [rows, C] into a channel slice
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ in, T* __restrict__ out, long long rows, int C, int out_ld, int out_coff) {
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows * cv) return;
+    const int c = static_cast<int>(i % cv) * V;
+    const long long r = i / cv;
+    *reinterpret_cast<uint4*>(out + r * out_ld + out_coff + c) = *reinterpret_cast<const uint4*>(in + r * C + c);
+}
+bool copy_channels_launch(const void* in, void* out, int rows, int C, int out_ld, int out_coff, int prec, cudaStream_t s) {
+    SB_DISPATCH_PREC(prec, {
+        const long long total = static_cast<long long>(rows) * (C / V16<T>::N);
+        copy_channels_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), rows, C, out_ld, out_coff);
+    });
+    return check_cuda(cudaGetLastError(), "copy_channels");
+}
+
+// ------------------------------------------------------------------ global average pool -> fp32 [N][out_ld]
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ in, float* __restrict__ out, int out_ld, int N, int HW, int C) {
+    constexpr int V = V16<T>::N;
+    const int cv = C / V;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(N) * cv) return;
+    const int c = static_cast<int>(i % cv) * V;
+    const long long n = i / cv;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    const T* p = in + n * HW * C + c;
+    for (int h = 0; h < HW; ++h) {
+        float f[V];
+        V16<T>::load(p + static_cast<size_t>(h) * C, f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += f[e];
+    }
+    const float inv = 1.f / static_cast<float>(HW);
+#pragma unroll
+    for (int e = 0; e < V; ++e) out[n * out_ld + c + e] = acc[e] * inv;
+}
+bool avgpool_launch(const void* in, float* out, int out_ld, int N, int HW, int C, int prec, cudaStream_t s) {
+    SB_DISPATCH_PREC(prec, {
+        const long long total = static_cast<long long>(N) * (C / V16<T>::N);
+        avgpool_kernel<T><<<nblk(total, 128), 128, 0, s>>>(static_cast<const T*>(in), out, out_ld, N, HW, C);
+    });
+    return check_cuda(cudaGetLastError(), "avgpool");
+}
+
+// ------------------------------------------------------------------ NHWC -> NCHW fp32 (backbone-only API)
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int N, int HW, int C) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(N) * HW * C) return;
+    const int hw = static_cast<int>(i % HW);
+    const long long t = i / HW;
+    const int c = static_cast<int>(t % C);
+    const long long n = t / C;
+    out[i] = DT<T>::to_f(in[(n * HW + hw) * C + c]);
+}
+bool nhwc_to_nchw_f32_launch(const void* in, float* out, int N, int H, int W, int C, int prec, cudaStream_t s) {
+    SB_DISPATCH_PREC(prec, {
+        const long long total = static_cast<long long>(N) * H * W * C;
+        nhwc_to_nchw_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), out, N, H * W, C);
+    });
+    return check_cuda(cudaGetLastError(), "nhwc_to_nchw");
+}
+
+}  // namespace sb

@@ -1,0 +1,62 @@
+// Internal (non-ABI) declarations shared by the .cu files of libspecb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+
+namespace sb {
+
+enum Precision { PREC_F32 = 0, PREC_BF16 = 1, PREC_F16 = 2 };
+
+// One convolution (+ folded-BN bias, + residual, + ReLU) over NHWC activations.
+struct ConvParams {
+    const void* in;      // [N,H,W,Cin]   (Cin dense)
+    void* out;           // [N,Ho,Wo,*]   channel stride out_ld, channel offset out_coff
+    const void* res;     // residual, same spatial/channel extent as the conv output; ld = res_ld; may be null
+    const float* bias;   // [Cout]
+    int N, H, W, Cin;
+    int Ho, Wo, Cout;
+    int kh, kw, stride, pad;
+    int K;               // kh*kw*Cin
+    int M;               // N*Ho*Wo
+    int out_ld, out_coff, res_ld;
+    int relu;
+};
+
+// Packed weights of one conv, owned by the trunk handle.
+struct ConvWeights {
+    int cout = 0, cin = 0, kh = 0, kw = 0;
+    int K = 0, K_pad = 0, cout_pad = 0, block_n = 0;
+    void* w_tc = nullptr;      // [cout_pad][K_pad] 16-bit, K-major (tcgen05 path)
+    float* w_f32 = nullptr;    // [K][cout] fp32 (SIMT parity path)
+    float* bias = nullptr;     // [cout]
+    CUtensorMap tmap_b;        // TMA descriptor over w_tc (box 64 x block_n, 128B swizzle)
+    bool has_tmap = false;
+};
+
+void set_error(const std::string& msg);
+bool check_cuda(cudaError_t e, const char* what);
+
+// tcgen05 implicit-GEMM conv (conv_tc.cu).  prec is PREC_BF16 or PREC_F16.
+bool conv_tc_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s);
+bool conv_tc_make_weight_tmap(ConvWeights& w);
+int conv_tc_pick_block_n(int cout);
+
+// fp32 SIMT implicit-GEMM conv and linear (conv_simt.cu).
+bool conv_f32_launch(const ConvParams& p, const ConvWeights& w, cudaStream_t s);
+// out[M, n0:n0+N] (ld out_ld) = A[M,K](ld lda) @ W[N,K]^T (ld ldw) + bias[N] + add[M,N](ld add_ld) ; fp32
+bool linear_f32_launch(const float* A, int lda, const float* W, int ldw, const float* bias, const float* add,
+                       int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s);
+
+// elementwise / layout kernels (elementwise.cu)
+bool images_to_nhwc_launch(const float* img_nchw, void* out_nhwc, int N, int H, int W, int cpad, int prec, cudaStream_t s);
+bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int prec, cudaStream_t s);
+bool upsample_add_launch(const void* lo, void* acc, int N, int Ho, int Wo, int C, int shift, int relu, int prec, cudaStream_t s);
+bool bilinear_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int out_ld, int out_coff,
+                     int prec, cudaStream_t s);
+bool copy_channels_launch(const void* in, void* out, int rows, int C, int out_ld, int out_coff, int prec, cudaStream_t s);
+bool avgpool_launch(const void* in, float* out, int out_ld, int N, int HW, int C, int prec, cudaStream_t s);
+bool nhwc_to_nchw_f32_launch(const void* in, float* out, int N, int H, int W, int C, int prec, cudaStream_t s);
+
+}  // namespace sb

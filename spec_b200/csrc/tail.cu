@@ -1,0 +1,474 @@
+// Fused fp32 "tail" kernels: everything after the backbone.
+//
+//  * CamCalib decode: soft-argmax over 256 bins -> angles -> f_pix, R = euler(pitch,0,roll), K
+//    (/root/reference/camcalib/cam_utils.py:110-145, scripts/camcalib_demo.py:127-129,
+//     spec/utils/cam_params.py:24-50)
+//  * HMR head state init (init_pose/shape/cam + camera features R6d, vfov;
+//    /root/reference/spec/models/hmr.py:95-96 and pare HMRHead)
+//  * SMPL: rot6d -> rotmat, rest joints, kinematic chain, pose/shape blendshapes + linear-blend
+//    skinning, 49-joint assembly, weak-perspective -> full-image camera, perspective projection
+//    (pare SMPLCamHead / smplx.lbs; call site spec/models/hmr.py:101-112)
+//
+// All HBM access is coalesced over the vertex index (SMPL constants are repacked coordinate-planar at
+// create time), reductions are warp shuffles, and every reduction order is fixed (deterministic output).
+#include "common.cuh"
+#include "internal.h"
+#include "tail.h"
+
+namespace sb {
+
+__constant__ int c_parents[24] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+// joint_map (49) and the 21 selected vertex ids are uploaded at create time (bit-exact integer tables).
+__constant__ int c_joint_map[49];
+__constant__ int c_vertex_ids[21];
+
+bool tail_upload_tables(const int* joint_map49, const int* vertex_ids21) {
+    if (!check_cuda(cudaMemcpyToSymbol(c_joint_map, joint_map49, 49 * sizeof(int)), "joint_map upload")) return false;
+    return check_cuda(cudaMemcpyToSymbol(c_vertex_ids, vertex_ids21, 21 * sizeof(int)), "vertex_ids upload");
+}
+
+// ------------------------------------------------------------------ CamCalib decode
+__device__ __forceinline__ void euler_to_rotmat(float ex, float ey, float ez, float* R) {
+    // batch_euler2matrix: euler -> quaternion (w,x,y,z) -> normalise -> matrix
+    const float hx = ex * 0.5f, hy = ey * 0.5f, hz = ez * 0.5f;
+    const float cx = cosf(hx), cy = cosf(hy), cz = cosf(hz);
+    const float sx = sinf(hx), sy = sinf(hy), sz = sinf(hz);
+    float qw = cx * cy * cz - sx * sy * sz;
+    float qx = cx * sy * sz + cy * cz * sx;
+    float qy = cx * cz * sy - sx * cy * sz;
+    float qz = cx * cy * sz + sx * cz * sy;
+    const float nrm = sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+    qw /= nrm; qx /= nrm; qy /= nrm; qz /= nrm;
+    const float w2 = qw * qw, x2 = qx * qx, y2 = qy * qy, z2 = qz * qz;
+    const float wx = qw * qx, wy = qw * qy, wz = qw * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
+    R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz;     R[2] = 2 * wy + 2 * xz;
+    R[3] = 2 * wz + 2 * xy;     R[4] = w2 - x2 + y2 - z2; R[5] = 2 * yz - 2 * wx;
+    R[6] = 2 * xz - 2 * wy;     R[7] = 2 * wx + 2 * yz;     R[8] = w2 - x2 - y2 + z2;
+}
+
+// grid = B, block = 96 (warp w decodes logits[:, w*D : (w+1)*D]).  logits row stride = ld.
+__global__ void __launch_bounds__(96)
+camcalib_decode_kernel(const float* __restrict__ logits, int ld, int D, const float* __restrict__ img_h,
+                       const float* __restrict__ img_w, float* __restrict__ angles, float* __restrict__ rotmat,
+                       float* __restrict__ intr, float* __restrict__ fpix, int B)
+{
+    __shared__ float s_ang[3];
+    const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* x = logits + static_cast<size_t>(b) * ld + w * D;
+    float mx = -INFINITY;
+    for (int i = lane; i < D; i += 32) mx = fmaxf(mx, x[i]);
+    mx = warp_max(mx);
+    float se = 0.f, sk = 0.f;
+    for (int i = lane; i < D; i += 32) {
+        const float e = expf(x[i] - mx);
+        se += e;
+        sk += e * static_cast<float>(i);
+    }
+    se = warp_sum(se);
+    sk = warp_sum(sk);
+    if (lane == 0) {
+        float k = sk / se;                                       // soft-argmax index
+        k = k / static_cast<float>(D - 1) * 2.f - 1.f;           // normalize_keypoints
+        const float lo = (w == 0) ? 0.2617f : -0.6f;             // cam_utils.py:55,39,133
+        const float hi = (w == 0) ? 2.1f : 0.6f;
+        const float range = (w == 0) ? static_cast<float>(2.1 - 0.2617) : static_cast<float>(0.6 - (-0.6));
+        s_ang[w] = range * ((k + 1.f) / 2.f) + lo;
+        (void)hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float vfov = s_ang[0], pitch = s_ang[1], roll = s_ang[2];
+        angles[b * 3 + 0] = vfov; angles[b * 3 + 1] = pitch; angles[b * 3 + 2] = roll;
+        if (rotmat != nullptr) {
+            const float h = img_h[b], wd = img_w[b];
+            const float f = h / 2.f / tanf(vfov / 2.f);          // camcalib_demo.py:129
+            float R[9];
+            euler_to_rotmat(pitch, 0.f, roll, R);                // cam_params.py:37
+            for (int i = 0; i < 9; ++i) rotmat[b * 9 + i] = R[i];
+            float* K = intr + b * 9;                             // cam_params.py:39-46 (K[2,2] stays 0)
+            K[0] = f; K[1] = 0.f; K[2] = wd / 2.f;
+            K[3] = 0.f; K[4] = f; K[5] = h / 2.f;
+            K[6] = 0.f; K[7] = 0.f; K[8] = 0.f;
+            if (fpix) fpix[b] = f;
+        }
+    }
+}
+
+bool camcalib_decode_launch(const float* logits, int ld, int D, const float* img_h, const float* img_w, float* angles,
+                            float* rotmat, float* intr, float* fpix, int B, cudaStream_t s) {
+    camcalib_decode_kernel<<<B, 96, 0, s>>>(logits, ld, D, img_h, img_w, angles, rotmat, intr, fpix, B);
+    return check_cuda(cudaGetLastError(), "camcalib_decode");
+}
+
+// ------------------------------------------------------------------ head state init
+// X row layout: [xf (C) | pose6d (144) | shape (10) | cam (3) | R6d (6) | vfov (1)]   (last 7 only with cam feats)
+__global__ void head_init_kernel(float* __restrict__ X, int ldx, int C, const float* __restrict__ init157,
+                                 const float* __restrict__ cam_rotmat, const float* __restrict__ cam_intr,
+                                 const float* __restrict__ img_h, int use_cam_feats, int B)
+{
+    const int b = blockIdx.x;
+    float* row = X + static_cast<size_t>(b) * ldx + C;
+    for (int i = threadIdx.x; i < 157; i += blockDim.x) row[i] = init157[i];
+    // zero the alignment padding behind the valid columns (the matching fc1 weight columns are zero,
+    // but 0 * garbage could still be NaN)
+    for (int i = 157 + (use_cam_feats ? 7 : 0) + threadIdx.x; i < ldx - C; i += blockDim.x) row[i] = 0.f;
+    if (use_cam_feats && threadIdx.x < 7) {
+        const int i = threadIdx.x;
+        float v;
+        if (i < 6) v = cam_rotmat[b * 9 + (i >> 1) * 3 + (i & 1)];                          // R[:, :2] row-major
+        else v = 2.f * atanf(img_h[b] / (2.f * cam_intr[b * 9]));                            // hmr.py:95
+        row[157 + i] = v;
+    }
+}
+bool head_init_launch(float* X, int ldx, int C, const float* init157, const float* cam_rotmat, const float* cam_intr,
+                      const float* img_h, int use_cam_feats, int B, cudaStream_t s) {
+    head_init_kernel<<<B, 64, 0, s>>>(X, ldx, C, init157, cam_rotmat, cam_intr, img_h, use_cam_feats, B);
+    return check_cuda(cudaGetLastError(), "head_init");
+}
+
+// ------------------------------------------------------------------ SMPL prep: rot6d, rest joints, kinematic chain
+// grid = B, block = 32.
+__global__ void __launch_bounds__(32)
+smpl_prep_kernel(const float* __restrict__ X, int ldx, int C, const float* __restrict__ Jt /*[24][3]*/,
+                 const float* __restrict__ Js /*[24][3][10]*/, float* __restrict__ pf /*[B][PF_LD]*/,
+                 float* __restrict__ Amat /*[B][24][12]*/, float* __restrict__ Jposed /*[B][24][3]*/,
+                 float* __restrict__ o_pose, long long ld_pose, float* __restrict__ o_pose6d, long long ld_pose6d,
+                 float* __restrict__ o_shape, long long ld_shape, float* __restrict__ o_cam, long long ld_cam, int B)
+{
+    __shared__ float sR[24][9];
+    __shared__ float sJ[24][3];
+    __shared__ float sG[24][12];
+    __shared__ float sBeta[10];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const float* st = X + static_cast<size_t>(b) * ldx + C;
+    if (lane < 10) sBeta[lane] = st[144 + lane];
+    for (int i = lane; i < 144; i += 32) o_pose6d[b * ld_pose6d + i] = st[i];
+    if (lane < 10) o_shape[b * ld_shape + lane] = st[144 + lane];
+    if (lane < 3) o_cam[b * ld_cam + lane] = st[154 + lane];
+    __syncwarp();
+    if (lane < 24) {
+        // rot6d_to_rotmat: x.view(3,2): a1 = x[:,0] = (x0,x2,x4), a2 = x[:,1] = (x1,x3,x5)
+        const float* x = st + lane * 6;
+        const float a1x = x[0], a1y = x[2], a1z = x[4];
+        const float a2x = x[1], a2y = x[3], a2z = x[5];
+        const float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-12f);
+        const float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+        const float d = b1x * a2x + b1y * a2y + b1z * a2z;
+        const float ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
+        const float n2 = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-12f);
+        const float b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+        const float b3x = b1y * b2z - b1z * b2y, b3y = b1z * b2x - b1x * b2z, b3z = b1x * b2y - b1y * b2x;
+        float* R = sR[lane];                                    // columns b1,b2,b3
+        R[0] = b1x; R[1] = b2x; R[2] = b3x;
+        R[3] = b1y; R[4] = b2y; R[5] = b3y;
+        R[6] = b1z; R[7] = b2z; R[8] = b3z;
+        float* op = o_pose + b * ld_pose + lane * 9;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) op[e] = R[e];
+        if (lane >= 1) {
+            float* p = pf + static_cast<size_t>(b) * PF_LD + (lane - 1) * 9;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) p[e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+        }
+        // rest joints J = Jt + Js . beta
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float acc = Jt[lane * 3 + c];
+#pragma unroll
+            for (int l = 0; l < 10; ++l) acc = fmaf(Js[(lane * 3 + c) * 10 + l], sBeta[l], acc);
+            sJ[lane][c] = acc;
+        }
+    }
+    if (lane == 0) pf[static_cast<size_t>(b) * PF_LD + 207] = 0.f;   // K padding column
+    __syncwarp();
+    // kinematic chain: G_0 = [R_0 | J_0];  G_i = G_par * [R_i | J_i - J_par]
+    if (lane < 9) sG[0][(lane / 3) * 4 + (lane % 3)] = sR[0][lane];
+    else if (lane < 12) sG[0][(lane - 9) * 4 + 3] = sJ[0][lane - 9];
+    __syncwarp();
+    for (int i = 1; i < 24; ++i) {
+        const int par = c_parents[i];
+        float v = 0.f;
+        if (lane < 9) {
+            const int r = lane / 3, c = lane % 3;
+            v = sG[par][r * 4 + 0] * sR[i][0 * 3 + c] + sG[par][r * 4 + 1] * sR[i][1 * 3 + c] + sG[par][r * 4 + 2] * sR[i][2 * 3 + c];
+        } else if (lane < 12) {
+            const int r = lane - 9;
+            const float rx = sJ[i][0] - sJ[par][0], ry = sJ[i][1] - sJ[par][1], rz = sJ[i][2] - sJ[par][2];
+            v = sG[par][r * 4 + 0] * rx + sG[par][r * 4 + 1] * ry + sG[par][r * 4 + 2] * rz + sG[par][r * 4 + 3];
+        }
+        __syncwarp();
+        if (lane < 9) sG[i][(lane / 3) * 4 + (lane % 3)] = v;
+        else if (lane < 12) sG[i][(lane - 9) * 4 + 3] = v;
+        __syncwarp();
+    }
+    if (lane < 24) {
+        const float* G = sG[lane];
+        float* A = Amat + (static_cast<size_t>(b) * 24 + lane) * 12;
+        const float jx = sJ[lane][0], jy = sJ[lane][1], jz = sJ[lane][2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            A[r * 4 + 0] = G[r * 4 + 0]; A[r * 4 + 1] = G[r * 4 + 1]; A[r * 4 + 2] = G[r * 4 + 2];
+            A[r * 4 + 3] = G[r * 4 + 3] - (G[r * 4 + 0] * jx + G[r * 4 + 1] * jy + G[r * 4 + 2] * jz);
+            Jposed[(static_cast<size_t>(b) * 24 + lane) * 3 + r] = G[r * 4 + 3];
+        }
+    }
+}
+
+bool smpl_prep_launch(const float* X, int ldx, int C, const float* Jt, const float* Js, float* pf, float* Amat,
+                      float* Jposed, float* o_pose, long long ld_pose, float* o_pose6d, long long ld_pose6d,
+                      float* o_shape, long long ld_shape, float* o_cam, long long ld_cam, int B, cudaStream_t s) {
+    smpl_prep_kernel<<<B, 32, 0, s>>>(X, ldx, C, Jt, Js, pf, Amat, Jposed, o_pose, ld_pose, o_pose6d, ld_pose6d,
+                                      o_shape, ld_shape, o_cam, ld_cam, B);
+    return check_cuda(cudaGetLastError(), "smpl_prep");
+}
+
+// ------------------------------------------------------------------ SMPL vertices
+// Tile: 64 vertices x 32 images per CTA; 256 threads: lane -> vertices (lane, lane+32), warp -> 4 images.
+constexpr int SV_TV = 64, SV_TB = 32, SV_BK = 16;
+struct SvSmem {
+    float A[SV_TB][24][12];          // skinning transforms of the tile's images (36 KB)
+    float P[SV_BK][3][SV_TV];        // posedirs chunk (12 KB)
+    float pf[SV_TB][SV_BK];          // pose-feature chunk
+    float beta[SV_TB][10];
+};
+
+__global__ void __launch_bounds__(256)
+smpl_verts_kernel(const float* __restrict__ Vt, const float* __restrict__ Sd, const float* __restrict__ Pd,
+                  const float* __restrict__ Wl, const float* __restrict__ Jx, const float* __restrict__ X, int ldx, int C,
+                  const float* __restrict__ pf, const float* __restrict__ Amat, float* __restrict__ o_verts,
+                  long long ld_verts, float* __restrict__ partials /*[B][NVT][27]*/, int B)
+{
+    extern __shared__ __align__(16) uint8_t sv_raw[];
+    SvSmem& sm = *reinterpret_cast<SvSmem*>(sv_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v0 = blockIdx.x * SV_TV;
+    const int b0 = blockIdx.y * SV_TB;
+
+    // stage per-image data
+    for (int i = tid; i < SV_TB * 288; i += 256) {
+        const int bi = i / 288, e = i - bi * 288;
+        reinterpret_cast<float*>(sm.A)[i] = (b0 + bi < B) ? Amat[static_cast<size_t>(b0 + bi) * 288 + e] : 0.f;
+    }
+    for (int i = tid; i < SV_TB * 10; i += 256) {
+        const int bi = i / 10, l = i - bi * 10;
+        sm.beta[bi][l] = (b0 + bi < B) ? X[static_cast<size_t>(b0 + bi) * ldx + C + 144 + l] : 0.f;
+    }
+
+    float acc[4][2][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[i][h][c] = 0.f;
+
+    // pose blendshapes: acc[img][vert][coord] = sum_p pf[img][p] * Pd[p][coord][vert]
+    for (int k0 = 0; k0 < PF_LD; k0 += SV_BK) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int idx = tid + q * 256;                     // 768 float4 = 16 x 3 x 64 floats
+            const int kk = idx / 48, rem = idx - kk * 48;
+            const int c = rem / 16, vq = (rem - c * 16) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + kk < 207)
+                v = *reinterpret_cast<const float4*>(Pd + (static_cast<size_t>(k0 + kk) * 3 + c) * SMPL_VP + v0 + vq);
+            *reinterpret_cast<float4*>(&sm.P[kk][c][vq]) = v;
+        }
+        if (tid < 128) {
+            const int bi = tid >> 2, kq = (tid & 3) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + bi < B) v = *reinterpret_cast<const float4*>(pf + static_cast<size_t>(b0 + bi) * PF_LD + k0 + kq);
+            *reinterpret_cast<float4*>(&sm.pf[bi][kq]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SV_BK; ++kk) {
+            float a[4], p[3][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sm.pf[warp * 4 + i][kk];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { p[c][0] = sm.P[kk][c][lane]; p[c][1] = sm.P[kk][c][lane + 32]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[i][h][c] = fmaf(a[i], p[c][h], acc[i][h][c]);
+        }
+    }
+
+    float ej[4][27];                                            // extra-joint partial sums of this thread
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 27; ++q) ej[i][q] = 0.f;
+
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int v = v0 + lane + 32 * h;
+        // shape blendshapes
+        float vs[4][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float t = Vt[static_cast<size_t>(c) * SMPL_VP + v];
+            float s[10];
+#pragma unroll
+            for (int l = 0; l < 10; ++l) s[l] = Sd[(static_cast<size_t>(l) * 3 + c) * SMPL_VP + v];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float sh = 0.f;
+#pragma unroll
+                for (int l = 0; l < 10; ++l) sh = fmaf(sm.beta[warp * 4 + i][l], s[l], sh);
+                vs[i][c] = (t + sh) + acc[i][h][c];             // v_posed = v_shaped + pose offsets
+            }
+        }
+        // skinning: T = sum_j w_j A_j  (3x4), v = T [v_posed; 1]
+        float T[4][12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 12; ++e) T[i][e] = 0.f;
+        for (int j = 0; j < 24; ++j) {
+            const float w = Wl[static_cast<size_t>(j) * SMPL_VP + v];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4* Aj = reinterpret_cast<const float4*>(&sm.A[warp * 4 + i][j][0]);
+                const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+                T[i][0] = fmaf(w, r0.x, T[i][0]); T[i][1] = fmaf(w, r0.y, T[i][1]); T[i][2] = fmaf(w, r0.z, T[i][2]); T[i][3] = fmaf(w, r0.w, T[i][3]);
+                T[i][4] = fmaf(w, r1.x, T[i][4]); T[i][5] = fmaf(w, r1.y, T[i][5]); T[i][6] = fmaf(w, r1.z, T[i][6]); T[i][7] = fmaf(w, r1.w, T[i][7]);
+                T[i][8] = fmaf(w, r2.x, T[i][8]); T[i][9] = fmaf(w, r2.y, T[i][9]); T[i][10] = fmaf(w, r2.z, T[i][10]); T[i][11] = fmaf(w, r2.w, T[i][11]);
+            }
+        }
+        float jx[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) jx[q] = Jx[static_cast<size_t>(q) * SMPL_VP + v];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float o[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                o[c] = T[i][c * 4 + 0] * vs[i][0] + T[i][c * 4 + 1] * vs[i][1] + T[i][c * 4 + 2] * vs[i][2] + T[i][c * 4 + 3];
+            const int b = b0 + warp * 4 + i;
+            if (b < B && v < SMPL_NV) {
+                float* dst = o_verts + b * ld_verts + static_cast<size_t>(v) * 3;
+                dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) ej[i][q * 3 + c] = fmaf(jx[q], o[c], ej[i][q * 3 + c]);
+        }
+    }
+    // extra-joint partials: reduce the tile's 64 vertices (fixed order), one record per (image, vertex tile)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int b = b0 + warp * 4 + i;
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
+            const float s = warp_sum(ej[i][q]);
+            if (lane == 0 && b < B) partials[(static_cast<size_t>(b) * SMPL_NVT + blockIdx.x) * 27 + q] = s;
+        }
+    }
+}
+
+bool smpl_verts_launch(const float* Vt, const float* Sd, const float* Pd, const float* Wl, const float* Jx, const float* X,
+                       int ldx, int C, const float* pf, const float* Amat, float* o_verts, long long ld_verts,
+                       float* partials, int B, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        if (!check_cuda(cudaFuncSetAttribute(smpl_verts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(SvSmem))), "smpl_verts attr")) return false;
+        attr = true;
+    }
+    dim3 grid(SMPL_NVT, (B + SV_TB - 1) / SV_TB);
+    smpl_verts_kernel<<<grid, 256, sizeof(SvSmem), s>>>(Vt, Sd, Pd, Wl, Jx, X, ldx, C, pf, Amat, o_verts, ld_verts, partials, B);
+    return check_cuda(cudaGetLastError(), "smpl_verts");
+}
+
+// ------------------------------------------------------------------ 49 joints, camera, projection
+// grid = B, block = 64.
+__global__ void __launch_bounds__(64)
+smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const float* __restrict__ Jposed,
+                   const float* __restrict__ partials, const float* __restrict__ X, int ldx, int C,
+                   const float* __restrict__ cam_rotmat, const float* __restrict__ cam_intr,
+                   const float* __restrict__ bbox_scale, const float* __restrict__ bbox_center,
+                   const float* __restrict__ img_w, const float* __restrict__ img_h,
+                   float* __restrict__ o_j3d, long long ld_j3d, float* __restrict__ o_j2d, long long ld_j2d,
+                   float* __restrict__ o_camt, long long ld_camt, int use_cam, float focal_length, float img_res, int B)
+{
+    __shared__ float j54[54][3];
+    __shared__ float s_t[3];
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (t < 24) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) j54[t][c] = Jposed[(static_cast<size_t>(b) * 24 + t) * 3 + c];
+    } else if (t < 45) {
+        const float* v = verts + b * ld_verts + static_cast<size_t>(c_vertex_ids[t - 24]) * 3;
+        j54[t][0] = v[0]; j54[t][1] = v[1]; j54[t][2] = v[2];
+    } else if (t < 54) {
+        const int q = t - 45;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        const float* p = partials + static_cast<size_t>(b) * SMPL_NVT * 27 + q * 3;
+        for (int vt = 0; vt < SMPL_NVT; ++vt) { s0 += p[vt * 27 + 0]; s1 += p[vt * 27 + 1]; s2 += p[vt * 27 + 2]; }
+        j54[t][0] = s0; j54[t][1] = s1; j54[t][2] = s2;
+    }
+    const float* cam = X + static_cast<size_t>(b) * ldx + C + 154;
+    if (t == 63) {
+        const float sc = cam[0], tx = cam[1], ty = cam[2];
+        float ct[3];
+        if (use_cam) {
+            // convert_pare_to_full_img_cam, bbox_height = bbox_scale * 200
+            const float bh = bbox_scale[b] * 200.f;
+            const float f = cam_intr[b * 9];
+            const float r = bh / img_res;
+            ct[2] = 2.f * f / (r * img_res * sc);
+            ct[0] = tx + 2.f * (bbox_center[b * 2 + 0] - img_w[b] / 2.f) / (sc * bh);
+            ct[1] = ty + 2.f * (bbox_center[b * 2 + 1] - img_h[b] / 2.f) / (sc * bh);
+        } else {
+            ct[0] = tx; ct[1] = ty; ct[2] = 2.f * focal_length / (img_res * sc + 1e-9f);
+        }
+        s_t[0] = ct[0]; s_t[1] = ct[1]; s_t[2] = ct[2];
+        o_camt[b * ld_camt + 0] = ct[0]; o_camt[b * ld_camt + 1] = ct[1]; o_camt[b * ld_camt + 2] = ct[2];
+    }
+    __syncthreads();
+    if (t < 49) {
+        const int src = c_joint_map[t];
+        const float x = j54[src][0], y = j54[src][1], z = j54[src][2];
+        float* o3 = o_j3d + b * ld_j3d + t * 3;
+        o3[0] = x; o3[1] = y; o3[2] = z;
+        float R[9], K[6];
+        if (use_cam) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = cam_rotmat[b * 9 + i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) K[i] = cam_intr[b * 9 + i];
+        } else {
+            R[0] = 1.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 1.f; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
+            K[0] = focal_length; K[1] = 0.f; K[2] = 0.f; K[3] = 0.f; K[4] = focal_length; K[5] = 0.f;
+        }
+        // perspective_projection
+        float px = R[0] * x + R[1] * y + R[2] * z + s_t[0];
+        float py = R[3] * x + R[4] * y + R[5] * z + s_t[1];
+        float pz = R[6] * x + R[7] * y + R[8] * z + s_t[2];
+        px = px / pz; py = py / pz; pz = pz / pz;
+        float u = K[0] * px + K[1] * py + K[2] * pz;
+        float v = K[3] * px + K[4] * py + K[5] * pz;
+        if (!use_cam) { u = u / (img_res / 2.f); v = v / (img_res / 2.f); }
+        o_j2d[b * ld_j2d + t * 2 + 0] = u;
+        o_j2d[b * ld_j2d + t * 2 + 1] = v;
+    }
+}
+
+bool smpl_joints_launch(const float* verts, long long ld_verts, const float* Jposed, const float* partials, const float* X,
+                        int ldx, int C, const float* cam_rotmat, const float* cam_intr, const float* bbox_scale,
+                        const float* bbox_center, const float* img_w, const float* img_h, float* o_j3d, long long ld_j3d,
+                        float* o_j2d, long long ld_j2d, float* o_camt, long long ld_camt, int use_cam, float focal_length,
+                        float img_res, int B, cudaStream_t s) {
+    smpl_joints_kernel<<<B, 64, 0, s>>>(verts, ld_verts, Jposed, partials, X, ldx, C, cam_rotmat, cam_intr, bbox_scale,
+                                        bbox_center, img_w, img_h, o_j3d, ld_j3d, o_j2d, ld_j2d, o_camt, ld_camt,
+                                        use_cam, focal_length, img_res, B);
+    return check_cuda(cudaGetLastError(), "smpl_joints");
+}
+
+}  // namespace sb

@@ -1,0 +1,283 @@
+"""``HMR`` -- drop-in for /root/reference/spec/models/hmr.py:28-122.
+
+Same constructor keywords, same ``forward(images, cam_rotmat, cam_intrinsics, bbox_scale, bbox_center,
+img_w, img_h)`` (positional order is part of the contract: spec/trainer.py:139), same output dict
+(``smpl_vertices (B,6890,3)``, ``smpl_joints3d (B,49,3)``, ``smpl_joints2d (B,49,2)``, ``pred_cam_t (B,3)``,
+``pred_pose (B,24,3,3)``, ``pred_cam (B,3)``, ``pred_shape (B,10)``, ``pred_pose_6d (B,144)`` -- fp32
+tensors on the input device, freshly allocated and writable), same state_dict names
+(``backbone.*``, ``head.fc1/fc2/decpose/decshape/deccam.*``, ``head.init_pose/init_shape/init_cam``,
+``smpl.smpl.*`` buffers).
+
+Parameter containers only; all arithmetic runs in libspecb200 (trunk kernels + the fused fp32 tail).
+"""
+import ctypes as C
+import os
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import backbone as _bb
+from .constants import JOINT_MAP_49, SMPL_VERTEX_IDS_21, SMPL_PARENTS
+from .synthetic import synthetic_smpl_data, synthetic_mean_params
+
+# where the reference keeps its assets (spec/config.py:35-38); all absent offline
+SMPL_MODEL_DIR = os.environ.get('SPECB200_SMPL_DIR', 'data/body_models/smpl')
+SMPL_MEAN_PARAMS = os.environ.get('SPECB200_SMPL_MEAN_PARAMS', 'data/smpl_mean_params.npz')
+JOINT_REGRESSOR_TRAIN_EXTRA = os.environ.get('SPECB200_J_REGRESSOR_EXTRA', 'data/J_regressor_extra.npy')
+
+
+def _load_smpl_data():
+    """SMPL constants from an .npz export under SMPL_MODEL_DIR if present, else seeded synthetic ones."""
+    npz = os.path.join(SMPL_MODEL_DIR, 'SMPL_NEUTRAL.npz')
+    if os.path.exists(npz) and os.path.exists(JOINT_REGRESSOR_TRAIN_EXTRA):
+        d = dict(np.load(npz))
+        out = {k: np.asarray(d[k], dtype=np.float32) for k in ('v_template', 'shapedirs', 'J_regressor')}
+        out['shapedirs'] = out['shapedirs'][:, :, :10]
+        pd = np.asarray(d['posedirs'], dtype=np.float32)
+        out['posedirs'] = pd.reshape(-1, pd.shape[-1]).T if pd.ndim == 3 else pd
+        out['lbs_weights'] = np.asarray(d['weights'] if 'weights' in d else d['lbs_weights'], dtype=np.float32)
+        out['J_regressor_extra'] = np.load(JOINT_REGRESSOR_TRAIN_EXTRA).astype(np.float32)
+        out['parents'] = np.asarray(SMPL_PARENTS, dtype=np.int64)
+        return out
+    warnings.warn(f'SMPL model not found under {SMPL_MODEL_DIR!r}: using seeded SYNTHETIC SMPL constants '
+                  '(right shapes, meaningless geometry)', stacklevel=3)
+    return synthetic_smpl_data(0)
+
+
+def _load_mean_params():
+    if os.path.exists(SMPL_MEAN_PARAMS):
+        d = np.load(SMPL_MEAN_PARAMS)
+        return {'pose': d['pose'].astype(np.float32), 'shape': d['shape'].astype(np.float32),
+                'cam': d['cam'].astype(np.float32)}
+    return synthetic_mean_params(0)
+
+
+class HMRHead(nn.Module):
+    """Parameter container of pare's HMRHead: fc1 (C+157[+7] -> 1024), fc2, three
+    decoders, ``init_*`` buffers (name evidenced at /root/reference/scripts/spec_eval.py:57)."""
+
+    def __init__(self, num_input_features, use_cam_feats=False, mean_params=None, **unused):
+        super().__init__()
+        npose = 144
+        self.npose = npose
+        self.use_cam_feats = use_cam_feats
+        self.num_input_features = num_input_features
+        self.fc1 = nn.Linear(num_input_features + npose + 13 + (7 if use_cam_feats else 0), 1024)
+        self.drop1 = nn.Dropout()
+        self.fc2 = nn.Linear(1024, 1024)
+        self.drop2 = nn.Dropout()
+        self.decpose = nn.Linear(1024, npose)
+        self.decshape = nn.Linear(1024, 10)
+        self.deccam = nn.Linear(1024, 3)
+        for m in (self.decpose, self.decshape, self.deccam):
+            nn.init.xavier_uniform_(m.weight, gain=0.01)
+        mp = mean_params if mean_params is not None else _load_mean_params()
+        self.register_buffer('init_pose', torch.as_tensor(mp['pose']).float().reshape(1, npose))
+        self.register_buffer('init_shape', torch.as_tensor(mp['shape']).float().reshape(1, 10))
+        self.register_buffer('init_cam', torch.as_tensor(mp['cam']).float().reshape(1, 3))
+
+    def forward(self, *a, **k):
+        raise RuntimeError('HMRHead is evaluated inside HMR.forward by libspecb200')
+
+
+class SMPL(nn.Module):
+    """Buffer container of pare.models.SMPL / smplx.SMPL (names as in smplx 0.1.28)."""
+
+    def __init__(self, smpl_data=None):
+        super().__init__()
+        d = smpl_data if smpl_data is not None else _load_smpl_data()
+        f = lambda k: torch.as_tensor(np.asarray(d[k])).float()
+        self.register_buffer('v_template', f('v_template'))
+        self.register_buffer('shapedirs', f('shapedirs'))
+        self.register_buffer('posedirs', f('posedirs'))
+        self.register_buffer('J_regressor', f('J_regressor'))
+        self.register_buffer('lbs_weights', f('lbs_weights'))
+        self.register_buffer('J_regressor_extra', f('J_regressor_extra'))
+        self.register_buffer('parents', torch.as_tensor(np.asarray(d['parents'])).long())
+        self.register_buffer('joint_map', torch.tensor(JOINT_MAP_49, dtype=torch.long))
+        self.register_buffer('vertex_ids', torch.tensor(SMPL_VERTEX_IDS_21, dtype=torch.long))
+        assert self.v_template.shape == (6890, 3) and self.posedirs.shape == (207, 20670)
+
+
+class SMPLCamHead(nn.Module):
+    def __init__(self, img_res=224, smpl_data=None):
+        super().__init__()
+        self.smpl = SMPL(smpl_data)
+        self.img_res = img_res
+
+
+class SMPLHead(nn.Module):
+    def __init__(self, focal_length=5000., img_res=224, smpl_data=None):
+        super().__init__()
+        self.smpl = SMPL(smpl_data)
+        self.focal_length = focal_length
+        self.img_res = img_res
+
+
+_OUT_SHAPES = {'smpl_vertices': (6890, 3), 'smpl_joints3d': (49, 3), 'smpl_joints2d': (49, 2), 'pred_cam_t': (3,),
+               'pred_pose': (24, 3, 3), 'pred_cam': (3,), 'pred_shape': (10,), 'pred_pose_6d': (144,)}
+
+
+class HMR(nn.Module):
+    def __init__(self, backbone='resnet50', focal_length=5000., img_res=224, pretrained=None, use_cam=False, p=0.0,
+                 estimate_var=False, use_separate_var_branch=False, uncertainty_activation='', use_cam_feats=False,
+                 smpl_data=None, mean_params=None):
+        super().__init__()
+        if estimate_var or use_separate_var_branch or uncertainty_activation:
+            raise NotImplementedError('uncertainty branches are never enabled on the SPEC hot path '
+                                      '(spec/tester.py:53-59, spec/trainer.py:50-56)')
+        if backbone.startswith('hrnet'):
+            backbone, use_conv = backbone.split('-')                     # hmr.py:44-51
+            self.backbone = getattr(_bb, backbone)(pretrained=True, downsample=True, use_conv=(use_conv == 'conv'))
+        else:
+            self.backbone = getattr(_bb, backbone)(pretrained=True)
+        self.use_cam_feats = use_cam_feats
+        self.head = HMRHead(num_input_features=_bb.get_backbone_info(backbone)['n_output_channels'],
+                            use_cam_feats=use_cam_feats, mean_params=mean_params)
+        self.use_cam = use_cam
+        if use_cam:
+            self.smpl = SMPLCamHead(img_res=img_res, smpl_data=smpl_data)
+        else:
+            self.smpl = SMPLHead(focal_length=focal_length, img_res=img_res, smpl_data=smpl_data)
+        self.focal_length, self.img_res = focal_length, img_res
+        self._handle = None
+        self._dirty = True
+        self._device = None
+        self._ws = None
+        self.register_load_state_dict_post_hook(lambda m, k: m._mark_dirty())
+        if pretrained is not None:
+            self.load_pretrained(pretrained)
+
+    # ---- checkpoint helpers (hmr.py:124-135)
+    def load_pretrained(self, file):
+        sd = torch.load(file, map_location='cpu')
+        sd = sd.get('model', sd.get('state_dict', sd))
+        sd = {k[len('model.'):] if k.startswith('model.') else k: v for k, v in sd.items()}
+        self.backbone.load_state_dict({k: v for k, v in sd.items() if k in self.backbone.state_dict()}, strict=False)
+        own = self.head.state_dict()
+        self.head.load_state_dict({k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}, strict=False)
+
+    # ---- engine
+    def _mark_dirty(self):
+        self._dirty = True
+
+    def _apply(self, fn, *a, **k):
+        self._dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.lib().specb200_hmrtail_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure(self, device):
+        if self._handle is not None and not self._dirty and self._device == device:
+            return
+        _lib.require_device()
+        self._release()
+        hd, sm = self.head, self.smpl.smpl
+        keep = []
+
+        def fp(t):
+            t = t.detach().float().contiguous().cpu()
+            keep.append(t)
+            return t.data_ptr()
+
+        def ip(t):
+            t = t.detach().to(torch.int32).contiguous().cpu()
+            keep.append(t)
+            return t.data_ptr()
+
+        p = _lib.HmrParams()
+        p.in_features = hd.num_input_features
+        p.use_cam_feats = int(self.use_cam_feats)
+        p.use_cam = int(self.use_cam)
+        p.focal_length = float(self.focal_length)
+        p.img_res = float(self.img_res)
+        p.fc1_w, p.fc1_b, p.fc2_w, p.fc2_b = fp(hd.fc1.weight), fp(hd.fc1.bias), fp(hd.fc2.weight), fp(hd.fc2.bias)
+        p.decpose_w, p.decpose_b = fp(hd.decpose.weight), fp(hd.decpose.bias)
+        p.decshape_w, p.decshape_b = fp(hd.decshape.weight), fp(hd.decshape.bias)
+        p.deccam_w, p.deccam_b = fp(hd.deccam.weight), fp(hd.deccam.bias)
+        p.init_pose, p.init_shape, p.init_cam = fp(hd.init_pose), fp(hd.init_shape), fp(hd.init_cam)
+        p.v_template, p.shapedirs, p.posedirs = fp(sm.v_template), fp(sm.shapedirs), fp(sm.posedirs)
+        p.J_regressor, p.lbs_weights, p.J_regressor_extra = fp(sm.J_regressor), fp(sm.lbs_weights), fp(sm.J_regressor_extra)
+        p.parents, p.joint_map, p.vertex_ids = ip(sm.parents), ip(sm.joint_map), ip(sm.vertex_ids)
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().specb200_hmrtail_create(C.byref(h), C.byref(p)))
+        self._handle = h
+        self._x_ld = int(_lib.lib().specb200_hmrtail_x_ld(h))
+        self._device = device
+        self._dirty = False
+
+    def _workspace(self, B, device):
+        n = _lib.lib().specb200_hmrtail_workspace_bytes(self._handle, B)
+        if self._ws is None or self._ws.numel() < n or self._ws.device != device:
+            self._ws = torch.empty(n, dtype=torch.uint8, device=device)
+        return self._ws
+
+    @staticmethod
+    def _f32(x, B, device, shape):
+        if x is None:
+            return None
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(x)
+        x = x.to(device=device, dtype=torch.float32)       # img_h / img_w arrive as int64 at trainer.py:239-240
+        return x.reshape((B,) + shape).contiguous()
+
+    def forward(self, images, cam_rotmat=None, cam_intrinsics=None, bbox_scale=None, bbox_center=None,
+                img_w=None, img_h=None, _out=None):
+        """``_out``: optional dict name -> (tensor view, per-image stride in floats) to write the outputs
+        into caller-provided (e.g. packed all-gather) storage instead of fresh tensors."""
+        _lib.require_device(images)
+        dev = images.device
+        B = images.shape[0]
+        if self.use_cam or self.use_cam_feats:
+            if cam_rotmat is None or cam_intrinsics is None or img_h is None:
+                raise ValueError('cam_rotmat, cam_intrinsics and img_h are required with use_cam / use_cam_feats')
+        if self.use_cam and (bbox_scale is None or bbox_center is None or img_w is None):
+            raise ValueError('bbox_scale, bbox_center and img_w are required with use_cam')
+        self._ensure(dev)
+        R = self._f32(cam_rotmat, B, dev, (3, 3))
+        K = self._f32(cam_intrinsics, B, dev, (3, 3))
+        bs = self._f32(bbox_scale, B, dev, ())
+        bc = self._f32(bbox_center, B, dev, (2,))
+        iw = self._f32(img_w, B, dev, ())
+        ih = self._f32(img_h, B, dev, ())
+        ws = self._workspace(B, dev)
+        # trunk writes the pooled feature straight into the head's input rows
+        self.backbone.run(images, pooled=ws.data_ptr(), pooled_ld=self._x_ld)
+        o = _lib.HmrOutputs()
+        result = {}
+        for key in _lib.OUTPUT_KEYS:
+            if _out is not None:
+                t, ld = _out[key]
+            else:
+                t = torch.empty((B,) + _OUT_SHAPES[key], dtype=torch.float32, device=dev)
+                ld = int(np.prod(_OUT_SHAPES[key]))
+            result[key] = t
+            setattr(o, key, t.data_ptr())
+            setattr(o, 'ld_' + key.split('_', 1)[1], ld)
+        ptr = lambda t: t.data_ptr() if t is not None else 0
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().specb200_hmrtail_forward(
+                self._handle, B, ws.data_ptr(), ws.numel(), ptr(R), ptr(K), ptr(bs), ptr(bc), ptr(iw), ptr(ih),
+                C.byref(o), torch.cuda.current_stream(dev).cuda_stream))
+        # same insertion order as the reference: smpl_output first, then updated with hmr_output (hmr.py:113)
+        return {k: result[k] for k in ('smpl_vertices', 'smpl_joints3d', 'smpl_joints2d', 'pred_cam_t',
+                                       'pred_pose', 'pred_cam', 'pred_shape', 'pred_pose_6d')}
+
+    def last_launches(self):
+        n = self.backbone.last_launches()
+        if self._handle is not None:
+            n += int(_lib.lib().specb200_hmrtail_last_launches(self._handle))
+        return n

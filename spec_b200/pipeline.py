@@ -1,0 +1,110 @@
+"""The full SPEC inference step as BASELINE.json times it: CamCalib(images) -> angles -> (R, K) ->
+HMR(images, R, K, boxes) -> packed per-image output record, optionally captured in one CUDA graph
+and sharded over ranks with ONE all-gather of the packed records.
+
+This replaces, in-process, the subprocess + pkl hand-off of the reference demo
+(/root/reference/spec/tester.py:86-88, spec/utils/cam_params.py:24-50) and the per-key
+``.cpu().numpy()`` loop (spec/tester.py:153-154).
+"""
+import torch
+
+from . import _lib
+from .constants import RECORD_LAYOUT, RECORD_FLOATS
+from .camcalib import CameraRegressorNetwork
+from .hmr import HMR
+
+_OFFSETS = {}
+_off = 0
+for _k, _n, _s in RECORD_LAYOUT:
+    _OFFSETS[_k] = (_off, _n, _s)
+    _off += _n
+
+
+def unpack_record(record):
+    """(B, RECORD_FLOATS) -> dict of strided views (no copy); works on the local or the gathered buffer."""
+    B = record.shape[0]
+    return {k: record[:, o:o + n].view((B,) + s) for k, (o, n, s) in _OFFSETS.items()}
+
+
+class SPECPipeline:
+    def __init__(self, camcalib: CameraRegressorNetwork, hmr: HMR, use_graph=True):
+        if not (hmr.use_cam and hmr.use_cam_feats):
+            raise ValueError('the SPEC pipeline uses HMR(use_cam=True, use_cam_feats=True) (spec/tester.py:53-59)')
+        self.camcalib, self.hmr = camcalib, hmr
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
+
+    # ---- eager
+    def _step(self, images, bbox_scale, bbox_center, img_w, img_h, record):
+        B = images.shape[0]
+        angles, R, K, _ = self.camcalib.predict_camera(images, img_h, img_w)
+        o, n, _ = _OFFSETS['cam_angles']
+        record[:, o:o + n].copy_(angles)
+        out = {k: (record[:, _OFFSETS[k][0]:_OFFSETS[k][0] + _OFFSETS[k][1]].view((B,) + _OFFSETS[k][2]), RECORD_FLOATS)
+               for k in _lib.OUTPUT_KEYS}
+        self.hmr(images, R, K, bbox_scale, bbox_center, img_w, img_h, _out=out)
+        return record
+
+    @torch.no_grad()
+    def forward_packed(self, images, bbox_scale, bbox_center, img_w, img_h):
+        """Returns the (B, 21294) fp32 record buffer.  With use_graph the buffer is reused between calls."""
+        _lib.require_device(images)
+        if not self.use_graph:
+            rec = torch.empty(images.shape[0], RECORD_FLOATS, dtype=torch.float32, device=images.device)
+            return self._step(images, bbox_scale, bbox_center, img_w, img_h, rec)
+        st = self._static
+        if st is None or st['images'].shape != images.shape or st['images'].device != images.device:
+            self._capture(images, bbox_scale, bbox_center, img_w, img_h)
+            st = self._static
+        st['images'].copy_(images, non_blocking=True)
+        st['bbox_scale'].copy_(bbox_scale, non_blocking=True)
+        st['bbox_center'].copy_(bbox_center, non_blocking=True)
+        st['img_w'].copy_(img_w, non_blocking=True)
+        st['img_h'].copy_(img_h, non_blocking=True)
+        self._graph.replay()
+        return st['record']
+
+    def _capture(self, images, bbox_scale, bbox_center, img_w, img_h):
+        dev = images.device
+        B = images.shape[0]
+        f = lambda t, shape: torch.empty((B,) + shape, dtype=torch.float32, device=dev).copy_(
+            torch.as_tensor(t).to(dev, torch.float32).reshape((B,) + shape))
+        st = {'images': images.detach().clone().float().contiguous(), 'bbox_scale': f(bbox_scale, ()),
+              'bbox_center': f(bbox_center, (2,)), 'img_w': f(img_w, ()), 'img_h': f(img_h, ()),
+              'record': torch.empty(B, RECORD_FLOATS, dtype=torch.float32, device=dev)}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                    # warm-up: packs weights, sizes workspaces, sets attributes
+            for _ in range(2):
+                self._step(st['images'], st['bbox_scale'], st['bbox_center'], st['img_w'], st['img_h'], st['record'])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step(st['images'], st['bbox_scale'], st['bbox_center'], st['img_w'], st['img_h'], st['record'])
+        self._graph, self._static = g, st
+
+    def __call__(self, images, bbox_scale, bbox_center, img_w, img_h):
+        return unpack_record(self.forward_packed(images, bbox_scale, bbox_center, img_w, img_h))
+
+    def launches_per_step(self):
+        """Kernels of libspecb200 enqueued by one step (trunk x2 + both tails + decode)."""
+        return self.camcalib.backbone.last_launches() + 2 + self.hmr.last_launches()
+
+
+def all_gather_records(record, group=None):
+    """ONE collective per step: every rank contributes its (B_local, 21294) record block; returns the
+    (world*B_local, 21294) buffer, rank-major (= image order under a contiguous batch split)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty(world * record.shape[0], record.shape[1], dtype=record.dtype, device=record.device)
+    dist.all_gather_into_tensor(out, record.contiguous(), group=group)
+    return out
+
+
+def shard_range(total, rank, world):
+    """Contiguous batch split: rank r owns images [lo, hi)."""
+    per = (total + world - 1) // world
+    lo = min(rank * per, total)
+    return lo, min(lo + per, total)

@@ -1,0 +1,125 @@
+"""CPU tests of the drop-in boundary: constructor / forward signatures and state_dict names equal the
+reference's (model.py:25-31,72; hmr.py:29-41,82-91), the C-ABI library loads and exports every symbol
+include/specb200.h declares, and the product refuses to compute without a GPU (no CPU fallback)."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import spec_b200 as sb
+from spec_b200 import _lib
+from tests.conftest import make_pair, make_camcalib_pair, ROOT
+
+
+def test_library_loads_and_exports_header_symbols():
+    hdr = open(os.path.join(ROOT, 'include', 'specb200.h')).read()
+    declared = set(re.findall(r'\b(specb200_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    import ctypes
+    l = ctypes.CDLL(_lib.LIB_PATH) if os.path.exists(_lib.LIB_PATH) else _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(l, name), f'{name} declared in specb200.h but not exported'
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.lib().specb200_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    import ctypes
+    assert ctypes.sizeof(_lib.Op) == 14 * 4
+    assert ctypes.sizeof(_lib.HmrOutputs) == 8 * 16
+    assert ctypes.sizeof(_lib.HmrParams) == 24 + 22 * 8
+
+
+def test_signatures_match_reference():
+    sig = inspect.signature(sb.CameraRegressorNetwork.__init__)
+    assert list(sig.parameters)[1:] == ['backbone', 'num_fc_layers', 'num_fc_channels', 'num_out_channels']
+    assert [p.default for p in list(sig.parameters.values())[1:]] == ['resnet50', 1, 1024, 256]
+    sig = inspect.signature(sb.HMR.__init__)
+    names = list(sig.parameters)[1:11]
+    assert names == ['backbone', 'focal_length', 'img_res', 'pretrained', 'use_cam', 'p', 'estimate_var',
+                     'use_separate_var_branch', 'uncertainty_activation', 'use_cam_feats']
+    fsig = inspect.signature(sb.HMR.forward)
+    assert list(fsig.parameters)[1:8] == ['images', 'cam_rotmat', 'cam_intrinsics', 'bbox_scale', 'bbox_center',
+                                          'img_w', 'img_h']        # positional order used at trainer.py:139
+    assert list(inspect.signature(sb.CameraRegressorNetwork.forward).parameters)[1:] == ['images']
+
+
+def test_reference_signatures_if_mounted():
+    """Parse the reference sources (dev container only) and compare argument lists literally."""
+    p = '/root/reference/spec/models/hmr.py'
+    if not os.path.exists(p):
+        pytest.skip('reference not mounted')
+    import ast
+    tree = ast.parse(open(p).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'HMR'][0]
+    fns = {f.name: [a.arg for a in f.args.args] for f in cls.body if isinstance(f, ast.FunctionDef)}
+    assert fns['forward'][1:] == list(inspect.signature(sb.HMR.forward).parameters)[1:8]
+    assert fns['__init__'][1:] == list(inspect.signature(sb.HMR.__init__).parameters)[1:11]
+    tree = ast.parse(open('/root/reference/camcalib/model.py').read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'CameraRegressorNetwork'][0]
+    fns = {f.name: [a.arg for a in f.args.args] for f in cls.body if isinstance(f, ast.FunctionDef)}
+    assert fns['__init__'][1:] == list(inspect.signature(sb.CameraRegressorNetwork.__init__).parameters)[1:]
+
+
+@pytest.mark.parametrize('backbone', ['resnet50', 'resnet34', 'hrnet_w32-conv', 'hrnet_w32-interp'])
+def test_state_dict_roundtrip_with_oracle(backbone):
+    prod, ref = make_pair(backbone)              # strict load inside
+    a, b = prod.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys()) or set(a) == set(b)
+    for k in ('head.init_pose', 'head.fc1.weight', 'backbone.conv1.weight', 'smpl.smpl.posedirs'):
+        assert k in a and a[k].shape == b[k].shape
+    exp_c = {'resnet50': 2048, 'resnet34': 512, 'hrnet_w32-conv': 480, 'hrnet_w32-interp': 480}[backbone]
+    assert a['head.fc1.weight'].shape == (1024, exp_c + 164)
+    if backbone == 'resnet50':
+        import torchvision
+        tv = set(k for k in torchvision.models.resnet50(weights=None).state_dict() if not k.startswith('fc.'))
+        assert tv == set(k[len('backbone.'):] for k in a if k.startswith('backbone.'))
+
+
+def test_camcalib_state_dict_and_multilayer():
+    prod, ref = make_camcalib_pair('resnet50')
+    assert set(prod.state_dict()) == set(ref.state_dict())
+    prod3, ref3 = make_camcalib_pair('resnet34', num_fc_layers=3)
+    assert set(prod3.state_dict()) == set(ref3.state_dict())
+    assert 'fc_vfov.2.weight' in prod3.state_dict()
+
+
+def test_flop_counts():
+    assert sb.resnet50().conv_flops_per_image() == 2 * 4087136256
+    assert sb.hrnet_w32().conv_flops_per_image() == 2 * 7917220864
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='CPU-only check')
+def test_no_cpu_fallback():
+    prod, _ = make_camcalib_pair('resnet34')
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        prod(torch.randn(1, 3, 64, 64))
+    h = sb.HMR('resnet34', use_cam=True, use_cam_feats=True)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        h(torch.randn(1, 3, 224, 224), torch.eye(3)[None], torch.eye(3)[None], torch.ones(1), torch.zeros(1, 2),
+          torch.ones(1), torch.ones(1))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        sb.decode_logits(torch.zeros(1, 768))
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never route through the oracle (test infrastructure)."""
+    pkg = os.path.join(ROOT, 'spec_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), fn
+            assert 'from oracle' not in src and 'import oracle' not in src, fn
+
+
+def test_record_layout_views():
+    rec = torch.arange(3 * sb.pipeline.RECORD_FLOATS, dtype=torch.float32).view(3, -1)
+    d = sb.unpack_record(rec)
+    assert d['smpl_vertices'].shape == (3, 6890, 3) and d['pred_pose'].shape == (3, 24, 3, 3)
+    assert d['smpl_vertices'].data_ptr() == rec.data_ptr()              # views, not copies
+    assert float(d['smpl_joints3d'][1, 0, 0]) == float(rec[1, 20670])
+    assert sum(v[0].numel() for v in d.values()) == sb.pipeline.RECORD_FLOATS
+    d['smpl_joints2d'][0, 0, 0] = -1.0                                  # writable (losses.py:191 mutates in place)
+    assert float(rec[0, 20670 + 147]) == -1.0

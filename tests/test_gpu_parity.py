@@ -1,0 +1,327 @@
+"""GPU parity tests (run on a B200 with ``pytest -m gpu``): the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs.
+
+Tolerances (north star, BASELINE.json): fp32 mode -- vertices <= 1e-3, camera parameters <= 1e-5, joint
+index tables bit-exact.  16-bit tensor-core modes are compared with the precision-matched oracle
+(oracle/lowp.py), tolerance stated per test.
+"""
+import numpy as np
+import pytest
+import torch
+
+import spec_b200 as sb
+from spec_b200.backbone import Trunk
+from spec_b200.synthetic import synthetic_batch, synthetic_camera, randomize_module_
+from spec_b200.constants import JOINT_MAP_49, SMPL_VERTEX_IDS_21
+from oracle import geometry as og
+from oracle import lowp
+from oracle.models import spec_full_forward
+from tests.conftest import make_pair, make_camcalib_pair
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TORCH_DT = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16}
+
+
+def _assert_close(name, got, ref, atol, rtol=0.0):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f'{name}: non-finite output'
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), f'{name}: max err {err.max().item():.3e} (tol {atol:g}+{rtol:g}*|ref|), {int(bad.sum())}/{bad.numel()} bad, ref scale {ref.abs().mean().item():.3e}'
+
+
+# --------------------------------------------------------------------------------------- building blocks
+def test_linear_f32_matches_torch():
+    import ctypes
+    from spec_b200 import _lib
+    torch.manual_seed(0)
+    for (M, N, K) in [(256, 1024, 2048), (7, 157, 1024), (33, 768, 512), (1, 64, 164)]:
+        a = torch.randn(M, K, device=DEV)
+        w = torch.randn(N, K, device=DEV) / K ** 0.5
+        b = torch.randn(N, device=DEV)
+        out = torch.empty(M, N, device=DEV)
+        _lib.check(_lib.lib().specb200_linear_f32(a.data_ptr(), K, w.data_ptr(), K, b.data_ptr(), out.data_ptr(), N, M, N, K,
+                                                  torch.cuda.current_stream().cuda_stream))
+        ref = (a.double() @ w.double().t() + b.double()).float()
+        _assert_close(f'linear {M}x{N}x{K}', out, ref, atol=2e-5, rtol=1e-5)
+
+
+def _mini(cmid, cout, k, stride, pad, res, precision):
+    def builder(root, P):
+        a = P.conv(root, 0, 3, cmid, 3, 1, 1, 'c0', 'b0', True)
+        r = P.conv(root, a, cmid, cout, k, stride, pad, 'cr', 'br', False) if res else None
+        b = P.conv(root, a, cmid, cout, k, stride, pad, 'c1', 'b1', True, res=r)
+        return b, cout
+    t = Trunk('custom', builder=builder, precision=precision)
+    randomize_module_(t, 3)
+    return t
+
+
+def _mini_ref(t, x, dtype, res):
+    a = lowp.conv_bn_act(lowp._rnd(x, dtype), t.c0, t.b0, dtype, True)
+    r = lowp.conv_bn_act(a, t.cr, t.br, dtype, False) if res else None
+    return lowp.conv_bn_act(a, t.c1, t.b1, dtype, True, res=r)
+
+
+CONV_CASES = [
+    # cmid, cout, k, stride, pad, res, H, W, B      what it exercises
+    (64, 64, 1, 1, 0, False, 16, 16, 2),            # 1x1: TMA A path, 1 k-block, BLOCK_N=64
+    (256, 128, 1, 1, 0, True, 12, 20, 3),           # 1x1 TMA A, 4 k-blocks, BLOCK_N=128, residual, ragged M
+    (64, 64, 3, 1, 1, False, 14, 14, 2),            # 3x3 gather, padding, 9 k-blocks
+    (128, 128, 3, 2, 1, False, 15, 17, 2),          # 3x3 stride 2, odd sizes
+    (64, 256, 1, 2, 0, False, 14, 14, 2),           # strided 1x1 (downsample) -> gather path
+    (32, 32, 3, 1, 1, True, 10, 10, 2),             # Cin=32 (HRNet): two taps per k-block, BLOCK_N=32
+    (64, 512, 1, 1, 0, False, 7, 7, 5),             # 4 N tiles
+]
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16', 'fp32'])
+@pytest.mark.parametrize('case', CONV_CASES, ids=[f'c{c[0]}-{c[1]}k{c[2]}s{c[3]}' for c in CONV_CASES])
+def test_conv_kernels(case, precision):
+    cmid, cout, k, stride, pad, res, H, W, B = case
+    t = _mini(cmid, cout, k, stride, pad, res, precision)
+    torch.manual_seed(1)
+    x = torch.randn(B, 3, H, W)
+    ref = _mini_ref(t, x, TORCH_DT[precision], res)
+    got = t.to(DEV)(x.to(DEV))
+    scale = ref.abs().mean().item()
+    if precision == 'fp32':
+        _assert_close('conv fp32', got, ref, atol=1e-4 * max(scale, 1.0), rtol=1e-4)
+    else:
+        # one 16-bit ulp (2^-8 bf16 / 2^-11 fp16) of slack for rounding-boundary flips from summation order
+        _assert_close(f'conv {precision}', got, ref, atol=0.02 * scale, rtol=0.02)
+
+
+def test_stem_conv7x7_and_maxpool():
+    for precision in ('bf16', 'fp32'):
+        def builder(root, P):
+            x = P.conv(root, 0, 3, 64, 7, 2, 3, 'conv1', 'bn1', True)
+            y = P.op(2, x, P.new(64))
+            return y, 64
+        t = Trunk('custom', builder=builder, precision=precision)
+        randomize_module_(t, 5)
+        x = torch.randn(2, 3, 64, 96)
+        dt = TORCH_DT[precision]
+        ref = torch.nn.functional.max_pool2d(lowp.conv_bn_act(lowp._rnd(x, dt), t.conv1, t.bn1, dt, True), 3, 2, 1)
+        got = t.to(DEV)(x.to(DEV))
+        s = ref.abs().mean().item()
+        _assert_close('stem ' + precision, got, ref, atol=(1e-4 if precision == 'fp32' else 0.02) * s, rtol=1e-4 if precision == 'fp32' else 0.02)
+
+
+# --------------------------------------------------------------------------------------- full path, fp32 parity mode
+def _run_product(cc, hmr, b, precision, graph=False):
+    cc.backbone.set_precision(precision)
+    hmr.backbone.set_precision(precision)
+    cc.to(DEV), hmr.to(DEV)
+    pipe = sb.SPECPipeline(cc, hmr, use_graph=graph)
+    bd = {k: v.to(DEV) for k, v in b.items()}
+    out = pipe(bd['images'], bd['bbox_scale'], bd['bbox_center'], bd['img_w'], bd['img_h'])
+    torch.cuda.synchronize()
+    return {k: v.clone() for k, v in out.items()}
+
+
+@pytest.fixture(scope='module')
+def models():
+    hmr, hmr_ref = make_pair('resnet50', seed=0)
+    cc, cc_ref = make_camcalib_pair('resnet50', seed=1)
+    return cc, cc_ref, hmr, hmr_ref
+
+
+def test_full_forward_fp32_parity(models):
+    cc, cc_ref, hmr, hmr_ref = models
+    b = synthetic_batch(4, seed=0)
+    ref = spec_full_forward(cc_ref, hmr_ref, b['images'], b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'])
+    got = _run_product(cc, hmr, b, 'fp32')
+    # camera parameters <= 1e-5 (north star)
+    ang_ref = torch.stack([ref['cam_vfov'], ref['cam_pitch'], ref['cam_roll']], 1)
+    _assert_close('cam angles', got['cam_angles'], ang_ref, atol=1e-5)
+    _assert_close('pred_cam', got['pred_cam'], ref['pred_cam'], atol=1e-5, rtol=1e-5)
+    # vertices <= 1e-3 (north star); the rest at comparable relative accuracy
+    _assert_close('smpl_vertices', got['smpl_vertices'], ref['smpl_vertices'], atol=1e-3)
+    _assert_close('smpl_joints3d', got['smpl_joints3d'], ref['smpl_joints3d'], atol=1e-3)
+    _assert_close('pred_pose', got['pred_pose'], ref['pred_pose'], atol=1e-4)
+    _assert_close('pred_pose_6d', got['pred_pose_6d'], ref['pred_pose_6d'], atol=1e-4, rtol=1e-4)
+    _assert_close('pred_shape', got['pred_shape'], ref['pred_shape'], atol=1e-4, rtol=1e-4)
+    _assert_close('pred_cam_t', got['pred_cam_t'], ref['pred_cam_t'], atol=1e-4, rtol=1e-4)
+    _assert_close('smpl_joints2d', got['smpl_joints2d'], ref['smpl_joints2d'], atol=0.05, rtol=1e-4)   # pixels
+
+
+def test_against_committed_golden(models):
+    """CUDA fp32 path vs tests/golden/spec_resnet50_b2.npz (oracle-made; see make_golden.py)."""
+    import os
+    from tests.golden.make_golden import build_models
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'spec_resnet50_b2.npz'))
+    cc_ref, hmr_ref = build_models(0)
+    cc = sb.CameraRegressorNetwork('resnet50'); cc.load_state_dict(cc_ref.state_dict())
+    hmr = sb.HMR('resnet50', use_cam=True, use_cam_feats=True); hmr.load_state_dict(hmr_ref.state_dict())
+    got = _run_product(cc, hmr, synthetic_batch(2, 0), 'fp32')
+    T = lambda k: torch.from_numpy(g[k])
+    _assert_close('golden vfov', got['cam_angles'][:, 0], T('cam_vfov'), atol=1e-5)
+    _assert_close('golden pitch', got['cam_angles'][:, 1], T('cam_pitch'), atol=1e-5)
+    _assert_close('golden roll', got['cam_angles'][:, 2], T('cam_roll'), atol=1e-5)
+    _assert_close('golden pred_cam', got['pred_cam'], T('pred_cam'), atol=1e-5, rtol=1e-5)
+    _assert_close('golden verts', got['smpl_vertices'][:, :64], T('smpl_vertices_first64'), atol=1e-3)
+    _assert_close('golden vert mean', got['smpl_vertices'].mean(1), T('smpl_vertices_mean'), atol=1e-4)
+    _assert_close('golden joints3d', got['smpl_joints3d'], T('smpl_joints3d'), atol=1e-3)
+    _assert_close('golden joints2d', got['smpl_joints2d'], T('smpl_joints2d'), atol=0.05, rtol=1e-4)
+
+
+def test_joint_gather_bit_exact(models):
+    """Integer tables are applied exactly: duplicated map entries are bit-identical, vertex-picked joints equal
+    the vertices they select, rotations are orthonormal."""
+    cc, _, hmr, _ = models
+    got = _run_product(cc, hmr, synthetic_batch(3, seed=2), 'fp32')
+    j3, v = got['smpl_joints3d'], got['smpl_vertices']
+    jm = JOINT_MAP_49
+    for a in range(49):
+        for c in range(a + 1, 49):
+            if jm[a] == jm[c]:
+                assert torch.equal(j3[:, a], j3[:, c]), (a, c)
+        if 24 <= jm[a] < 45:
+            assert torch.equal(j3[:, a], v[:, SMPL_VERTEX_IDS_21[jm[a] - 24]]), a
+    R = got['pred_pose'].reshape(-1, 3, 3)
+    assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3, device=R.device).expand_as(R), atol=1e-5)
+    assert torch.allclose(torch.linalg.det(R), torch.ones(R.shape[0], device=R.device), atol=1e-5)
+
+
+# --------------------------------------------------------------------------------------- 16-bit tensor-core modes
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+def test_full_forward_lowp_parity(models, precision):
+    cc, cc_ref, hmr, hmr_ref = models
+    dt = TORCH_DT[precision]
+    b = synthetic_batch(4, seed=0)
+    lg = lowp.camcalib_lowp(cc_ref, b['images'], dt)
+    vfov, pitch, roll = og.convert_preds_to_angles(*lg)
+    R, K, _ = og.cam_params_from_angles(vfov, pitch, roll, b['img_h'], b['img_w'])
+    ref = lowp.hmr_lowp(hmr_ref, b['images'], R, K, b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'], dt)
+    got = _run_product(cc, hmr, b, precision)
+    # tolerance: the emulation rounds at the same points; what is left is fp32 summation order, which can flip a
+    # 16-bit rounding (1 ulp = 2^-8 bf16) on isolated activations -> ~1e-3 relative on pooled features.
+    _assert_close('cam angles', got['cam_angles'], torch.stack([vfov, pitch, roll], 1), atol=2e-3)
+    _assert_close('pred_cam', got['pred_cam'], ref['pred_cam'], atol=5e-3, rtol=5e-3)
+    _assert_close('smpl_vertices', got['smpl_vertices'], ref['smpl_vertices'], atol=1e-2)
+    _assert_close('pred_pose', got['pred_pose'], ref['pred_pose'], atol=1e-2)
+
+
+def test_lowp_vs_fp32_oracle_deviation_is_small(models):
+    """Sanity: bf16 stays near the fp32 oracle (reported, loose bound: SURVEY.md 7.2 measured ~3% of feature std)."""
+    cc, cc_ref, hmr, hmr_ref = models
+    b = synthetic_batch(2, seed=3)
+    ref = spec_full_forward(cc_ref, hmr_ref, b['images'], b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'])
+    got = _run_product(cc, hmr, b, 'bf16')
+    err = (got['smpl_vertices'].cpu() - ref['smpl_vertices']).abs().max().item()
+    assert err < 0.15, err
+
+
+# --------------------------------------------------------------------------------------- other backbones
+@pytest.mark.parametrize('backbone', ['hrnet_w32-conv', 'hrnet_w32-interp', 'resnet34'])
+def test_other_backbones_fp32(backbone):
+    hmr, ref = make_pair(backbone, seed=4)
+    b = synthetic_batch(2, seed=4)
+    vfov, pitch, roll = synthetic_camera(2, seed=4)
+    R, K, _ = og.cam_params_from_angles(vfov, pitch, roll, b['img_h'], b['img_w'])
+    with torch.no_grad():
+        want = ref(b['images'], R, K, b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'])
+        feat_ref = ref.backbone(b['images'])
+    hmr.backbone.set_precision('fp32')
+    hmr.to(DEV)
+    feat = hmr.backbone(b['images'].to(DEV))
+    _assert_close('features', feat, feat_ref, atol=1e-3 * feat_ref.abs().mean().item(), rtol=1e-3)
+    got = hmr(b['images'].to(DEV), R.to(DEV), K.to(DEV), b['bbox_scale'].to(DEV), b['bbox_center'].to(DEV),
+              b['img_w'].to(DEV), b['img_h'].to(DEV))
+    _assert_close('smpl_vertices', got['smpl_vertices'], want['smpl_vertices'], atol=1e-3)
+    _assert_close('pred_cam', got['pred_cam'], want['pred_cam'], atol=1e-5, rtol=1e-5)
+
+
+def test_hrnet_bf16_runs_close():
+    hmr, ref = make_pair('hrnet_w32-conv', seed=4)
+    x = synthetic_batch(2, seed=4)['images']
+    with torch.no_grad():
+        feat_ref = ref.backbone(x)
+    hmr.backbone.set_precision('bf16')
+    feat = hmr.to(DEV).backbone(x.to(DEV))
+    rel = ((feat.cpu() - feat_ref).abs().mean() / feat_ref.abs().mean()).item()
+    assert rel < 0.05, rel
+
+
+def test_camcalib_module_forward_and_variable_size():
+    """CameraRegressorNetwork.forward returns three (B,256) logit tensors; non-224 inputs work (the demo feeds
+    min-side-600 images, camcalib_demo.py:95-102)."""
+    cc, ref = make_camcalib_pair('resnet50', seed=1)
+    cc.backbone.set_precision('fp32')
+    cc.to(DEV)
+    x = torch.randn(1, 3, 192, 256)
+    with torch.no_grad():
+        want = ref(x)
+    got = cc(x.to(DEV))
+    assert isinstance(got, list) and len(got) == 3 and all(g.shape == (1, 256) for g in got)
+    for g, w in zip(got, want):
+        _assert_close('logits', g, w, atol=2e-5, rtol=1e-4)
+    a = sb.convert_preds_to_angles(*got, loss_type='softargmax_l2')
+    wa = og.convert_preds_to_angles(*want)
+    for g, w in zip(a, wa):
+        _assert_close('angles', g, w, atol=1e-5)
+    # multi-layer FC variant (model.py:54-70)
+    cc3, ref3 = make_camcalib_pair('resnet34', seed=2, num_fc_layers=3)
+    cc3.backbone.set_precision('fp32')
+    x = torch.randn(2, 3, 224, 224)
+    with torch.no_grad():
+        want = ref3(x)
+    got = cc3.to(DEV)(x.to(DEV))
+    for g, w in zip(got, want):
+        _assert_close('logits3', g, w, atol=1e-4, rtol=1e-3)
+
+
+# --------------------------------------------------------------------------------------- consumer contract / properties
+def test_consumer_shim_contract(models):
+    """Replays what spec/tester.py:143-167 and spec/trainer.py:235-254,348-353 do with the outputs."""
+    _, _, hmr, _ = models
+    hmr.backbone.set_precision('bf16')
+    hmr.to(DEV)
+    b = synthetic_batch(3, seed=5, device=DEV)
+    vfov, pitch, roll = synthetic_camera(3, seed=5)
+    R, K, _ = og.cam_params_from_angles(vfov, pitch, roll, b['img_h'].cpu(), b['img_w'].cpu())
+    img_h_int = b['img_h'].long()                       # trainer.py:239-240 passes integer tensors
+    img_w_int = b['img_w'].long()
+    out = hmr(b['images'], R.to(DEV), K.to(DEV), b['bbox_scale'], b['bbox_center'], img_w_int, img_h_int)   # positional
+    assert list(out.keys()) == ['smpl_vertices', 'smpl_joints3d', 'smpl_joints2d', 'pred_cam_t', 'pred_pose',
+                                'pred_cam', 'pred_shape', 'pred_pose_6d']
+    shapes = {'smpl_vertices': (3, 6890, 3), 'smpl_joints3d': (3, 49, 3), 'smpl_joints2d': (3, 49, 2), 'pred_cam_t': (3, 3),
+              'pred_pose': (3, 24, 3, 3), 'pred_cam': (3, 3), 'pred_shape': (3, 10), 'pred_pose_6d': (3, 144)}
+    for k, v in out.items():
+        assert isinstance(v, torch.Tensor) and v.dtype == torch.float32 and v.device.type == 'cuda'
+        assert tuple(v.shape) == shapes[k]
+        assert np.isfinite(v.cpu().numpy()).all()                       # tester.py:153-154
+    out['smpl_joints2d'][:, :, 0] /= 224.                               # losses.py:191 in-place write
+    _ = out['pred_pose'][:, 1:].contiguous(), out['pred_pose'][:, 0].unsqueeze(1).contiguous()   # trainer.py:251-252
+    _ = out['smpl_joints3d'][:, 25:]                                    # losses.py:335
+
+
+def test_graph_equals_eager_and_is_deterministic(models):
+    cc, _, hmr, _ = models
+    b = synthetic_batch(8, seed=6)
+    e = _run_product(cc, hmr, b, 'bf16', graph=False)
+    g1 = _run_product(cc, hmr, b, 'bf16', graph=True)
+    g2 = _run_product(cc, hmr, b, 'bf16', graph=True)
+    for k in e:
+        assert torch.equal(e[k], g1[k]), k
+        assert torch.equal(g1[k], g2[k]), k
+
+
+def test_batch_composition_invariance_at_full_size(models):
+    """Size-independent property at BASELINE's B=256: an image's result does not depend on its position in the
+    batch or on the batch size (every image is independent through the whole path)."""
+    cc, _, hmr, _ = models
+    big = synthetic_batch(256, seed=7)
+    out_big = _run_product(cc, hmr, big, 'bf16')
+    idx = [0, 127, 128, 255]
+    small = {k: v[idx] for k, v in big.items()}
+    out_small = _run_product(cc, hmr, small, 'bf16')
+    for k in out_big:
+        assert torch.equal(out_big[k][idx], out_small[k]), k
+    R = out_big['pred_pose'].reshape(-1, 3, 3)
+    assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3, device=R.device).expand_as(R), atol=1e-5)
+    assert torch.isfinite(out_big['smpl_vertices']).all()
