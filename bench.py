@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the SPEC full forward (CamCalib -> (R,K) -> HMR -> SMPL -> projection),
+224x224, batch 256 per GPU (BASELINE.json configs[2]; weak scaling over GPUs), synthetic data, random weights.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5              # our arm (B200, libspecb200)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W               # N ranks, one per GPU, NCCL all-gather of records
+  python bench.py --impl reference --steps 3 --warmup 3       # the reference path's CPU restatement (oracle)
+
+Prints ONE JSON line (contract in the task statement): value = whole-job images/s with inputs resident in HBM,
+e2e = same metric through the public API with pinned-host inputs (H2D and D2H inside the timed region),
+roofline = conv FLOPs / event-timed conv-kernel time against the measured bf16 peak, cpu_baseline = the oracle
+on the host cores for a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+warnings.simplefilter('ignore')
+
+import torch  # noqa: E402
+
+METRIC = 'images/sec SPEC fwd (224^2, b256)'
+UNIT = 'images/s'
+CONV_FLOPS_PER_IMAGE = {'resnet50': 2 * 4087136256}           # SURVEY.md B.1, per trunk
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tf_burst': d['bf16_tflops'], 'tf_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(', '))
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            pass
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit())
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(n)
+        mx = max((float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()), default=None)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# =============================================================================================== reference arm / cpu baseline
+def build_oracle(backbone):
+    from oracle import models as om
+    from spec_b200.synthetic import synthetic_smpl_data, synthetic_mean_params, randomize_module_
+    torch.manual_seed(0)
+    hmr = om.HMR(backbone, use_cam=True, use_cam_feats=True, smpl_data=synthetic_smpl_data(0),
+                 mean_params=synthetic_mean_params(0)).eval()
+    randomize_module_(hmr.backbone, 0)
+    cc = om.CameraRegressorNetwork('resnet50').eval()
+    randomize_module_(cc.backbone, 1)
+    return cc, hmr
+
+
+def time_oracle(backbone, sample, steps, warmup):
+    """Oracle (CPU restatement of the reference path) on all host cores; returns (images/s, ms per sample step)."""
+    from oracle.models import spec_full_forward
+    from spec_b200.synthetic import synthetic_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cc, hmr = build_oracle(backbone)
+    b = synthetic_batch(sample, 0)
+    args = (b['images'], b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'])
+    for _ in range(warmup):
+        spec_full_forward(cc, hmr, *args)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        spec_full_forward(cc, hmr, *args)
+    dt = time.perf_counter() - t0
+    return sample * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return                                                  # other ranks exit 0 without work
+    sample = a.cpu_sample
+    ips, ms, cores = time_oracle(a.backbone, sample, a.steps, a.warmup)
+    desc = f'{sample} of {a.batch} images per step (bounded CPU sample), fp32 PyTorch oracle, {cores} threads'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
+        'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'SPEC full forward (CamCalib->{a.backbone}->HMR head->SMPL->proj), 224x224, batch {a.batch}',
+                   'backbone': a.backbone, 'note': 'reference arithmetic (pare/smplx) is not installable offline; this is its CPU restatement (oracle/)'},
+        'cpu_baseline': {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+        'e2e': {'value': ips, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+# =============================================================================================== our arm
+def run_ours(a):
+    import torch.distributed as dist
+    import spec_b200 as sb
+    from spec_b200.synthetic import synthetic_batch, randomize_module_
+    from spec_b200.constants import RECORD_FLOATS
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != a.gpus:
+        raise SystemExit(f'--gpus {a.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    B = a.batch                                                   # per-GPU batch (weak scaling)
+    cc = sb.CameraRegressorNetwork('resnet50')
+    randomize_module_(cc.backbone, 1)
+    hmr = sb.HMR(a.backbone, use_cam=True, use_cam_feats=True)
+    randomize_module_(hmr.backbone, 0)
+    for m in (cc, hmr):
+        m.backbone.set_precision(a.precision)
+        m.backbone.chunk = a.chunk
+        m.to(dev)
+    pipe = sb.SPECPipeline(cc, hmr, use_graph=not a.no_graph)
+    b = synthetic_batch(B, seed=rank, device=dev)                 # each rank generates its own shard
+    args = (b['images'], b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'])
+
+    def step():
+        rec = pipe.forward_packed(*args)
+        if world > 1:
+            return sb.all_gather_records(rec)                     # the ONE collective of the data path
+        return rec
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)             # max over ranks
+        return ms.item()
+
+    # ---- value: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step, a.steps, a.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / a.steps
+    value = world * B * a.steps / (total_ms * 1e-3)
+    launches_per_step = pipe.launches_per_step()
+
+    # ---- e2e: public API with HOST (pinned) inputs, H2D + D2H inside the timed region
+    host = {k: v.cpu().pin_memory() for k, v in b.items()}
+    host_rec = torch.empty(B, RECORD_FLOATS, dtype=torch.float32).pin_memory()
+    dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+
+    def e2e_step():
+        for k in dbuf:
+            dbuf[k].copy_(host[k], non_blocking=True)
+        rec = pipe.forward_packed(dbuf['images'], dbuf['bbox_scale'], dbuf['bbox_center'], dbuf['img_w'], dbuf['img_h'])
+        if world > 1:
+            rec = sb.all_gather_records(rec)[rank * B:(rank + 1) * B]
+        host_rec.copy_(rec, non_blocking=True)
+
+    e2e_steps = max(3, min(a.steps, 10))
+    e2e_ms = timed(e2e_step, e2e_steps, 3)
+    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = host_rec.numel() * 4
+
+    out = None
+    if rank == 0:
+        # ---- roofline: per-op CUDA-event timing of both trunks (live, eager, on the launching stream)
+        peaks = load_peaks()
+        conv_ms, conv_flops, step_ops_ms = 0.0, 0.0, 0.0
+        for m in (cc, hmr):
+            m.backbone.profile_ops(b['images'])                   # warm
+            rows = m.backbone.profile_ops(b['images'])
+            conv_ms += sum(r['ms'] for r in rows if r['flops'] > 0)
+            conv_flops += sum(r['flops'] for r in rows)
+            step_ops_ms += sum(r['ms'] for r in rows)
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+        n_conv = sum(1 for m in (cc, hmr) for o in m.backbone._program.ops if o['type'] == 1)
+        # ---- cpu baseline (bounded sample, rank 0, N=1 only)
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            ips, _, cores = time_oracle(a.backbone, a.cpu_sample, 2, 1)
+            cpu = {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                   'sample': f'{a.cpu_sample}-image batches x2 of the same workload, fp32 PyTorch oracle (oracle/), {cores} threads'}
+        out = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': a.precision, 'data': 'synthetic',
+            'config': {'workload': f'SPEC full forward (CamCalib resnet50 -> (R,K) -> HMR {a.backbone} -> SMPL -> projection), 224x224, batch {B}/GPU, random weights',
+                       'backbone': a.backbone, 'batch_per_gpu': B, 'global_batch': B * world, 'cuda_graph': not a.no_graph,
+                       'l2': 'inputs 154 MB/step/GPU > 126 MB L2, no explicit flush (weights stay L2-resident as in steady-state serving)',
+                       'parallelism': f'dp{world} (batch shard + one all-gather of 85,176 B/image records)' if world > 1 else 'single GPU'},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / e2e_steps},
+            'gpu_launches': int(launches_per_step * a.steps),
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
+                         'frac': achieved / peaks['tf_sustained'], 'traffic': None,
+                         'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)' % n_conv,
+                         'how': 'sum of conv FLOPs of both trunks / sum of per-launch CUDA-event times (specb200_trunk_profile, eager, same stream)',
+                         'peak_source': peaks['source'] + ' bf16 sustained', 'conv_ms_per_step': conv_ms,
+                         'conv_share_of_trunk_ops': conv_ms / step_ops_ms if step_ops_ms else None,
+                         'step_frac_of_peak': (world * 0 + conv_flops) / (ms_per_step * 1e-3) / 1e12 / peaks['tf_sustained']},
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
+    ap.add_argument('--backbone', default='resnet50')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32'])
+    ap.add_argument('--chunk', type=int, default=int(os.environ.get('SPECB200_CHUNK', '0')))
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample', type=int, default=16, help='images per CPU-oracle step (bounded sample)')
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == '__main__':
+    main()

@@ -83,6 +83,13 @@ int specb200_trunk_forward(specb200_trunk_t* t, const float* images_nchw_dev, in
                            float* feat_nchw_out_dev, void* stream);
 /* number of kernels the last forward enqueued (bench.py's gpu_launches) */
 int64_t specb200_trunk_last_launches(specb200_trunk_t* t);
+int32_t specb200_trunk_num_ops(specb200_trunk_t* t);
+/* Diagnostic variant of specb200_trunk_forward: brackets every op with CUDA events on `stream`, SYNCHRONISES, and
+ * writes per-op device milliseconds to op_ms_host[0 .. n_ops+1] (0 = image NCHW->NHWC conversion, 1..n_ops = ops in
+ * program order, n_ops+1 = average pool), summed over batch chunks.  Used by bench.py for the live roofline. */
+int specb200_trunk_profile(specb200_trunk_t* t, const float* images_nchw_dev, int32_t batch, int32_t h, int32_t w,
+                           void* workspace_dev, int64_t workspace_bytes, float* pooled_out_dev, int32_t pooled_ld,
+                           float* op_ms_host, void* stream);
 void specb200_trunk_destroy(specb200_trunk_t* t);
 
 /* ---- CamCalib tail: fc_vfov/fc_pitch/fc_roll (model.py:77-81) + convert_preds_to_angles

@@ -57,6 +57,9 @@ _PROTOS = {
     'specb200_trunk_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'specb200_trunk_last_launches': (C.c_int64, [C.c_void_p]),
+    'specb200_trunk_num_ops': (C.c_int32, [C.c_void_p]),
+    'specb200_trunk_profile': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'specb200_trunk_destroy': (None, [C.c_void_p]),
     'specb200_camtail_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     'specb200_camtail_add_linear': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

@@ -372,6 +372,55 @@ class Trunk(nn.Module):
     def last_launches(self):
         return int(_lib.lib().specb200_trunk_last_launches(self._handle)) if self._handle else 0
 
+    def profile_ops(self, images):
+        """Per-op device milliseconds (CUDA events on the current stream; synchronises).  Returns a list of dicts
+        with op geometry, algorithmic FLOPs / bytes and measured time -- the live per-layer roofline table."""
+        import numpy as np
+        _lib.require_device(images)
+        images = images.contiguous()
+        B, _, H, W = images.shape
+        self._ensure(images.device)
+        ws = self._workspace(B, H, W, images.device)
+        pooled = torch.empty(B, self.n_output_channels, dtype=torch.float32, device=images.device)
+        n = len(self._program.ops)
+        ms = np.zeros(n + 2, dtype=np.float32)
+        with torch.cuda.device(images.device):
+            _lib.check(_lib.lib().specb200_trunk_profile(
+                self._handle, images.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), pooled.data_ptr(),
+                self.n_output_channels, ms.ctypes.data, torch.cuda.current_stream(images.device).cuda_stream))
+        es = 4 if self.precision == 'fp32' else 2
+        shapes = {0: (H, W)}
+        rows = [dict(name='images_to_nhwc', type=0, ms=float(ms[0]), flops=0, bytes=B * H * W * (12 + es * (4 if es == 4 else 8)))]
+        for i, o in enumerate(self._program.ops):
+            sh = shapes[o['src']]
+            r = dict(type=o['type'], ms=float(ms[i + 1]), flops=0)
+            if o['type'] == OP_CONV:
+                ho = (sh[0] + 2 * o['pad'] - o['kh']) // o['stride'] + 1
+                wo = (sh[1] + 2 * o['pad'] - o['kw']) // o['stride'] + 1
+                cin = 3 if o['src'] == 0 else o['cin']
+                cin_s = (4 if es == 4 else 8) if o['src'] == 0 else o['cin']
+                r.update(name=self._program.convs[o['wslot']][0], cin=cin, cout=o['cout'], k=o['kh'], stride=o['stride'],
+                         hin=sh[0], hout=ho, flops=2 * B * ho * wo * o['cout'] * cin * o['kh'] * o['kw'],
+                         bytes=es * (B * sh[0] * sh[1] * cin_s + B * ho * wo * o['cout'] * (2 if o['src2'] >= 0 else 1)
+                                     + o['cout'] * cin_s * o['kh'] * o['kw']))
+                shapes[o['dst']] = (ho, wo)
+            elif o['type'] == OP_MAXPOOL:
+                shapes[o['dst']] = ((sh[0] - 1) // 2 + 1, (sh[1] - 1) // 2 + 1)
+                c = self._program.buf_ch[o['src']]
+                r.update(name='maxpool', bytes=es * B * c * (sh[0] * sh[1] + shapes[o['dst']][0] * shapes[o['dst']][1]))
+            elif o['type'] == OP_BILINEAR:
+                shapes[o['dst']] = shapes[o['src2']]
+                r.update(name='bilinear', bytes=0)
+            elif o['type'] == OP_COPY:
+                shapes[o['dst']] = sh
+                r.update(name='copy', bytes=2 * es * B * sh[0] * sh[1] * self._program.buf_ch[o['src']])
+            else:
+                d = shapes[o['dst']]
+                r.update(name='upadd', bytes=es * B * self._program.buf_ch[o['dst']] * (2 * d[0] * d[1] + sh[0] * sh[1]))
+            rows.append(r)
+        rows.append(dict(name='avgpool', type=0, ms=float(ms[n + 1]), flops=0, bytes=0))
+        return rows
+
     def forward(self, images):
         """``self.backbone(images)`` of the reference: the final NCHW fp32 feature map."""
         return self.run(images, want_features=True)

@@ -42,6 +42,8 @@ struct specb200_trunk {
     int prec = PREC_BF16;
     int chunk = 0;
     int64_t last_launches = 0;
+    std::vector<cudaEvent_t> prof_ev;        // non-empty only inside specb200_trunk_profile
+    size_t prof_n = 0;
     // cached plan
     int plan_h = -1, plan_w = -1;
     std::vector<BufShape> op_src, op_dst;    // per-op spatial dims
@@ -223,10 +225,13 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
     }
     int64_t launches = 0;
     const int C_out = t->buf_ch[t->out_buf];
+    auto mark = [&]() { if (!t->prof_ev.empty() && t->prof_n < t->prof_ev.size()) cudaEventRecord(t->prof_ev[t->prof_n++], s); };
     for (int b0 = 0; b0 < batch; b0 += eb) {
         const int nb = std::min(eb, batch - b0);
+        mark();
         if (!images_to_nhwc_launch(images + static_cast<size_t>(b0) * 3 * h * w, buf[0], nb, h, w, t->buf_ch[0], t->prec, s)) return 1;
         ++launches;
+        mark();
         for (size_t i = 0; i < t->ops.size(); ++i) {
             const specb200_op_t& o = t->ops[i];
             const BufShape sS = t->op_src[i], dS = t->op_dst[i];
@@ -265,11 +270,13 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
                 default: set_error("trunk_forward: unknown op"); return 1;
             }
             ++launches;
+            mark();
         }
         if (pooled_out) {
             if (!avgpool_launch(buf[t->out_buf], pooled_out + static_cast<size_t>(b0) * pooled_ld, pooled_ld, nb, t->out_h * t->out_w, C_out, t->prec, s)) return 1;
             ++launches;
         }
+        mark();
         if (feat_out) {
             if (!nhwc_to_nchw_f32_launch(buf[t->out_buf], feat_out + static_cast<size_t>(b0) * C_out * t->out_h * t->out_w, nb, t->out_h, t->out_w, C_out, t->prec, s)) return 1;
             ++launches;
@@ -280,6 +287,35 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
 }
 
 extern "C" int64_t specb200_trunk_last_launches(specb200_trunk_t* t) { return t ? t->last_launches : 0; }
+
+extern "C" int32_t specb200_trunk_num_ops(specb200_trunk_t* t) { return t ? static_cast<int32_t>(t->ops.size()) : 0; }
+
+extern "C" int specb200_trunk_profile(specb200_trunk_t* t, const float* images, int32_t batch, int32_t h, int32_t w,
+                                      void* workspace, int64_t workspace_bytes, float* pooled_out, int32_t pooled_ld,
+                                      float* op_ms_host, void* stream) {
+    if (!t || !op_ms_host) { set_error("trunk_profile: bad arguments"); return 1; }
+    const int eb = trunk_eff_batch(t, batch);
+    const size_t per_chunk = t->ops.size() + 3;                // start, after image conversion, after each op, after pool
+    const size_t chunks = (batch + eb - 1) / eb;
+    t->prof_ev.resize(per_chunk * chunks);
+    for (auto& e : t->prof_ev) if (!check_cuda(cudaEventCreate(&e), "cudaEventCreate")) return 1;
+    t->prof_n = 0;
+    int rc = specb200_trunk_forward(t, images, batch, h, w, workspace, workspace_bytes, pooled_out, pooled_ld, nullptr, stream);
+    if (rc == 0 && !check_cuda(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "sync")) rc = 1;
+    if (rc == 0) {
+        for (size_t i = 0; i + 1 < per_chunk; ++i) op_ms_host[i] = 0.f;
+        for (size_t c = 0; c < chunks; ++c)
+            for (size_t i = 0; i + 1 < per_chunk; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, t->prof_ev[c * per_chunk + i], t->prof_ev[c * per_chunk + i + 1]);
+                op_ms_host[i] += ms;
+            }
+    }
+    for (auto& e : t->prof_ev) cudaEventDestroy(e);
+    t->prof_ev.clear();
+    t->prof_n = 0;
+    return rc;
+}
 
 extern "C" void specb200_trunk_destroy(specb200_trunk_t* t) {
     if (!t) return;

@@ -232,7 +232,9 @@ def test_other_backbones_fp32(backbone):
     _assert_close('features', feat, feat_ref, atol=1e-3 * feat_ref.abs().mean().item(), rtol=1e-3)
     got = hmr(b['images'].to(DEV), R.to(DEV), K.to(DEV), b['bbox_scale'].to(DEV), b['bbox_center'].to(DEV),
               b['img_w'].to(DEV), b['img_h'].to(DEV))
-    _assert_close('smpl_vertices', got['smpl_vertices'], want['smpl_vertices'], atol=1e-3)
+    # random-init HRNet features are large, so the (amplified) head regresses |verts| ~ 70 here: the 1e-3 absolute
+    # bound is kept for metre-scale values and scaled relatively above that
+    _assert_close('smpl_vertices', got['smpl_vertices'], want['smpl_vertices'], atol=1e-3, rtol=1e-4)
     _assert_close('pred_cam', got['pred_cam'], want['pred_cam'], atol=1e-5, rtol=1e-5)
 
 
