@@ -6,14 +6,21 @@
 //
 // GEMM view:  D[M, Cout] = A[M, K] * W[Cout, K]^T,  M = N*Ho*Wo output pixels, K = kh*kw*Cin with
 // k = (tap, channel).  Activations are NHWC 16-bit, weights K-major 16-bit (BN folded), accumulation
-// fp32 in tensor memory.  One CTA computes a 128 x BLOCK_N output tile:
+// fp32 in tensor memory.  One CTA computes a 128 x BLOCK_N output tile.
 //
-//   warps 0-3  A producers: software im2col -- thread t owns tile row t and copies its 128-byte
-//              K-slice per stage with zero-filling cp.async straight into the 128B-swizzled layout
-//              the UMMA descriptor expects (1x1/stride-1 convs skip this: A is a plain [M,Cin]
-//              matrix and comes in by TMA).  Afterwards the same warps run the epilogue:
-//              tcgen05.ld accumulator rows -> +bias (+residual) -> ReLU -> 16-bit NHWC store.
-//   warp 4     TMA producer for the weight tile (and the A tile in TMA_A mode); owns TMEM alloc.
+// A operand (128 pixels x 64 channels per pipeline stage, 128B-swizzled K-major rows):
+//   A_TILED   1x1 stride-1 convs: A is the plain [M, Cin] matrix -> TMA tiled 2-D load.
+//   A_IM2COL  any conv with Cin % 64 == 0: TMA im2col-mode load straight from the NHWC tensor (the
+//             hardware walks output pixels, applies the filter-tap offset and zero-fills the padding).
+//   A_GATHER  everything else (the 3-channel stem, Cin = 32): warps 0-3 do the im2col in software
+//             with zero-filling cp.async into the same swizzled layout.
+// B operand: TMA tiled 2-D load of the [Cout, K] weight matrix.
+//
+//   warps 0-3  (A_GATHER producers, then) epilogue: tcgen05.ld accumulator rows -> +bias (+residual)
+//              -> ReLU -> 16-bit.  EPI_TMA: the residual tile is TMA-loaded into the (by then free)
+//              pipeline smem, combined in place, and the finished tile leaves through a TMA store --
+//              fully coalesced 128-byte lines in both directions.  BLOCK_N = 32 keeps direct stores.
+//   warp 4     TMA producer (A and B); owns the TMEM allocation.
 //   warp 5     MMA issuer: one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage and
 //              commits stage release / accumulator-ready to mbarriers.
 //
@@ -29,27 +36,38 @@ constexpr int TILE_K = 64;                      // 64 x 16-bit = 128 B = one swi
 constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;
 constexpr int GATHER_LAG = 2;                   // cp.async groups kept in flight per producer thread
 constexpr int CONV_TC_THREADS = 192;
+enum { A_TILED = 0, A_IM2COL = 1, A_GATHER = 2 };
 
 template <int BLOCK_N, int STAGES>
 struct ConvTcSmem {
     static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-    static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;          // full[STAGES], empty[STAGES], tmem_full
-    static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
+    static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;          // full[STAGES], empty[STAGES], tmem_full, res_full
+    static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 2) * 8;
     static constexpr int BIAS_OFF = TMEMPTR_OFF + 8;
     static constexpr int TOTAL = BIAS_OFF + BLOCK_N * 4;
     static constexpr int DYN_BYTES = TOTAL + 1024;                           // slack for manual 1024 B alignment
+    static constexpr int EPI_BYTES = TILE_M * BLOCK_N * 2;                   // output staging tile (aliases the A stages)
+    static_assert(EPI_BYTES <= STAGES * A_STAGE_BYTES, "staging tile must fit in the A stages");
 };
 
-template <typename T, int BLOCK_N, int STAGES, bool TMA_A>
+struct ConvTcMaps {
+    CUtensorMap a;      // A_TILED: [M][Cin] tiled;  A_IM2COL: NHWC im2col;  A_GATHER: unused
+    CUtensorMap b;      // weights [Cout_pad][K_pad]
+    CUtensorMap out;    // EPI_TMA: [M][out_ld] box 64 x 128
+    CUtensorMap res;    // EPI_TMA + residual: [M][res_ld] box 64 x 128
+};
+
+template <typename T, int BLOCK_N, int STAGES, int A_MODE>
 __global__ void __launch_bounds__(CONV_TC_THREADS)
-conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
-               const __grid_constant__ CUtensorMap tmap_b, int n_tiles)
+conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int n_tiles)
 {
     static_assert(GATHER_LAG <= STAGES - 1, "producer lag must leave one free stage");
     using L = ConvTcSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr bool EPI_TMA_CAPABLE = BLOCK_N >= 64;
+    const bool epi_tma = EPI_TMA_CAPABLE && (p.Cout & 63) == 0;   // whole 64-column boxes only (concat slices stay intact)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -58,6 +76,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t bar_full = sbase + L::BAR_OFF;
     const uint32_t bar_empty = bar_full + STAGES * 8;
     const uint32_t bar_tmem = bar_empty + STAGES * 8;
+    const uint32_t bar_res = bar_tmem + 8;
     volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sgen + L::TMEMPTR_OFF);
     float* sbias = reinterpret_cast<float*>(sgen + L::BIAS_OFF);
 
@@ -71,10 +90,11 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
     // ---------------- one-time setup
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + s * 8, TMA_A ? 1 : 5);      // 4 gather warps + the TMA thread
+            mbar_init(bar_full + s * 8, A_MODE == A_GATHER ? 5 : 1);   // 4 gather warps + the TMA thread
             mbar_init(bar_empty + s * 8, 1);
         }
         mbar_init(bar_tmem, 1);
+        mbar_init(bar_res, 1);
         mbar_fence_init();
     }
     if (threadIdx.x < BLOCK_N) {
@@ -83,8 +103,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
     }
     if (warp == 4) {
         if (lane == 0) {
-            tma_prefetch_desc(&tmap_b);
-            if (TMA_A) tma_prefetch_desc(&tmap_a);
+            tma_prefetch_desc(&maps.b);
+            if (A_MODE != A_GATHER) tma_prefetch_desc(&maps.a);
+            if (epi_tma) { tma_prefetch_desc(&maps.out); if (p.res != nullptr) tma_prefetch_desc(&maps.res); }
         }
         __syncwarp();
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), TMEM_COLS);
@@ -100,7 +121,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
         const long long r = static_cast<long long>(m_tile) * TILE_M + t;
         const bool row_ok = r < p.M;
         // ---------------- A producer (software im2col)
-        if constexpr (!TMA_A) {
+        if constexpr (A_MODE == A_GATHER) {
             const T* __restrict__ in = static_cast<const T*>(p.in);
             int n = 0, oh = 0, ow = 0;
             if (row_ok) {
@@ -164,45 +185,102 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
             }
         }
         // ---------------- epilogue
-        mbar_wait(bar_tmem, 0);
+        mbar_wait(bar_tmem, 0);                                   // all MMAs retired: accumulator ready, pipeline smem free
         tc_fence_after();
-        T* __restrict__ out = static_cast<T*>(p.out);
-        const T* __restrict__ res = static_cast<const T*>(p.res);
-        const size_t out_row = static_cast<size_t>(r) * p.out_ld + p.out_coff;
-        const size_t res_row = static_cast<size_t>(r) * p.res_ld;
+        if (epi_tma) {
+            const uint32_t stage_tile = a_base;                   // [BLOCK_N/64][128 rows][128 B], 128B-swizzled
+            const bool has_res = p.res != nullptr;
+            if (has_res) {
+                if (t == 0) {
+                    mbar_arrive_expect_tx(bar_res, L::EPI_BYTES);
+#pragma unroll
+                    for (int bx = 0; bx < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++bx)
+                        tma_load_2d(stage_tile + bx * (TILE_M * 128), &maps.res, bar_res, n0 + bx * 64, m_tile * TILE_M);
+                }
+                mbar_wait(bar_res, 0);
+            }
+            const uint32_t row_addr = stage_tile + static_cast<uint32_t>(t) * 128u;
+            const uint32_t sw = static_cast<uint32_t>(t) & 7u;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
-            tmem_ld_wait();
-            if (row_ok) {
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+                tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int col = n0 + c * 32 + q * 8;
-                    if (col < p.Cout) {
-                        float f[8];
+                    const int col = c * 32 + q * 8;               // column inside the tile
+                    const uint32_t addr = row_addr + (col >> 6) * (TILE_M * 128) + ((((col & 63) >> 3) ^ sw) << 4);
+                    float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + sbias[c * 32 + q * 8 + e];
-                        if (res != nullptr) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(res + res_row + col);
-                            const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + sbias[col + e];
+                    if (has_res) {
+                        uint32_t ru[4];
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ru[0]), "=r"(ru[1]), "=r"(ru[2]), "=r"(ru[3]) : "r"(addr));
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 rf = DT<T>::unpack2(ru[e]);
-                                f[2 * e] += rf.x;
-                                f[2 * e + 1] += rf.y;
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 rf = DT<T>::unpack2(ru[e]);
+                            f[2 * e] += rf.x;
+                            f[2 * e + 1] += rf.y;
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                    }
+                    const uint32_t o0 = DT<T>::pack2(f[0], f[1]), o1 = DT<T>::pack2(f[2], f[3]);
+                    const uint32_t o2 = DT<T>::pack2(f[4], f[5]), o3 = DT<T>::pack2(f[6], f[7]);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                }
+            }
+            fence_proxy_async_smem();                             // generic-proxy smem writes -> TMA store reads
+            named_bar_sync(1, 128);
+            if (t == 0) {
+#pragma unroll
+                for (int bx = 0; bx < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++bx)
+                    if (n0 + bx * 64 < p.Cout)
+                        tma_store_2d(&maps.out, stage_tile + bx * (TILE_M * 128), p.out_coff + n0 + bx * 64, m_tile * TILE_M);
+                tma_store_commit();
+                tma_store_wait_read0();                           // smem must stay valid until the store has read it
+            }
+        } else {
+            T* __restrict__ out = static_cast<T*>(p.out);
+            const T* __restrict__ res = static_cast<const T*>(p.res);
+            const size_t out_row = static_cast<size_t>(r) * p.out_ld + p.out_coff;
+            const size_t res_row = static_cast<size_t>(r) * p.res_ld;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int col = n0 + c * 32 + q * 8;
+                        if (col < p.Cout) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + sbias[c * 32 + q * 8 + e];
+                            if (res != nullptr) {
+                                const uint4 rv = *reinterpret_cast<const uint4*>(res + res_row + col);
+                                const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 rf = DT<T>::unpack2(ru[e]);
+                                    f[2 * e] += rf.x;
+                                    f[2 * e + 1] += rf.y;
+                                }
                             }
-                        }
-                        if (p.relu) {
+                            if (p.relu) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                            }
+                            uint4 ov;
+                            ov.x = DT<T>::pack2(f[0], f[1]);
+                            ov.y = DT<T>::pack2(f[2], f[3]);
+                            ov.z = DT<T>::pack2(f[4], f[5]);
+                            ov.w = DT<T>::pack2(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(out + out_row + col) = ov;
                         }
-                        uint4 ov;
-                        ov.x = DT<T>::pack2(f[0], f[1]);
-                        ov.y = DT<T>::pack2(f[2], f[3]);
-                        ov.z = DT<T>::pack2(f[4], f[5]);
-                        ov.w = DT<T>::pack2(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(out + out_row + col) = ov;
                     }
                 }
             }
@@ -210,14 +288,33 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
     } else if (warp == 4) {
         // ---------------- TMA producer
         if (lane == 0) {
-            constexpr uint32_t tx_bytes = L::B_STAGE_BYTES + (TMA_A ? A_STAGE_BYTES : 0);
+            constexpr uint32_t tx_bytes = L::B_STAGE_BYTES + (A_MODE != A_GATHER ? A_STAGE_BYTES : 0);
+            int pw = 0, ph = 0, pn = 0;                           // im2col base pixel of the tile's first row
+            if constexpr (A_MODE == A_IM2COL) {
+                const long long r0 = static_cast<long long>(m_tile) * TILE_M;
+                const int hw = p.Ho * p.Wo;
+                pn = static_cast<int>(r0 / hw);
+                const int rem = static_cast<int>(r0 - static_cast<long long>(pn) * hw);
+                const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+                pw = ow * p.stride - p.pad;
+                ph = oh * p.stride - p.pad;
+            }
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const int it = kb / STAGES;
                 mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
                 mbar_arrive_expect_tx(bar_full + s * 8, tx_bytes);
-                tma_load_2d(b_base + s * L::B_STAGE_BYTES, &tmap_b, bar_full + s * 8, kb * TILE_K, n0);
-                if (TMA_A) tma_load_2d(a_base + s * A_STAGE_BYTES, &tmap_a, bar_full + s * 8, kb * TILE_K, m_tile * TILE_M);
+                tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
+                if constexpr (A_MODE == A_TILED) {
+                    tma_load_2d(a_base + s * A_STAGE_BYTES, &maps.a, bar_full + s * 8, kb * TILE_K, m_tile * TILE_M);
+                } else if constexpr (A_MODE == A_IM2COL) {
+                    const int k0 = kb * TILE_K;
+                    const int tap = k0 / p.Cin;
+                    const int c0 = k0 - tap * p.Cin;
+                    const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+                    tma_load_im2col_4d(a_base + s * A_STAGE_BYTES, &maps.a, bar_full + s * 8, c0, pw, ph, pn,
+                                       static_cast<uint16_t>(kwi), static_cast<uint16_t>(khi));
+                }
             }
         }
         __syncwarp();
@@ -257,27 +354,28 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
+static void* get_driver_fn(const char* name) {
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    cudaError_t e = cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
-        set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+        set_error(std::string("cudaGetDriverEntryPoint(") + name + ") failed");
         return nullptr;
     }
-    fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    return fn;
+    return ptr;
 }
 
-// 2-D 16-bit row-major tensor [rows][cols], box = 64 cols x box_rows rows, 128-byte swizzle.
-static bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-    EncodeTiledFn fn = get_encode_fn();
+// 2-D 16-bit row-major tensor [rows][ld] viewed as cols columns; box = 64 cols x box_rows rows, 128-byte swizzle.
+static bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) fn = reinterpret_cast<EncodeTiledFn>(get_driver_fn("cuTensorMapEncodeTiled"));
     if (!fn) return false;
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * 2};
+    cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {TILE_K, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -285,6 +383,29 @@ static bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (code " + std::to_string(static_cast<int>(r)) + ")");
+        return false;
+    }
+    return true;
+}
+
+// NHWC activation tensor in im2col mode: 64 channels x 128 output pixels per load.
+static bool make_tmap_im2col(CUtensorMap* m, const ConvParams& p) {
+    static EncodeIm2colFn fn = nullptr;
+    if (!fn) fn = reinterpret_cast<EncodeIm2colFn>(get_driver_fn("cuTensorMapEncodeIm2col"));
+    if (!fn) return false;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cin), static_cast<cuuint64_t>(p.W), static_cast<cuuint64_t>(p.H),
+                          static_cast<cuuint64_t>(p.N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cin) * 2, static_cast<cuuint64_t>(p.W) * p.Cin * 2,
+                             static_cast<cuuint64_t>(p.H) * p.W * p.Cin * 2};
+    // bounding box of the filter's top-left corner ("base pixel"): [-pad, dim - 1 + pad - (k-1)]
+    int lower[2] = {-p.pad, -p.pad};
+    int upper[2] = {p.pad - (p.kw - 1), p.pad - (p.kh - 1)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(p.stride), static_cast<cuuint32_t>(p.stride), 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(p.in), dims, strides, lower, upper,
+                    TILE_K, TILE_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col failed (code " + std::to_string(static_cast<int>(r)) + ")");
         return false;
     }
     return true;
@@ -298,38 +419,52 @@ int conv_tc_pick_block_n(int cout) {
 
 bool conv_tc_make_weight_tmap(ConvWeights& w) {
     if (!make_tmap_2d(&w.tmap_b, w.w_tc, static_cast<uint64_t>(w.cout_pad), static_cast<uint64_t>(w.K_pad),
-                      static_cast<uint32_t>(w.block_n)))
+                      static_cast<uint64_t>(w.K_pad), static_cast<uint32_t>(w.block_n)))
         return false;
     w.has_tmap = true;
     return true;
 }
 
+static int g_force_gather = -1;     // SPECB200_FORCE_GATHER=1 disables the TMA im2col path (debug / A-B test)
+
 template <typename T, int BLOCK_N, int STAGES>
 static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s) {
     using L = ConvTcSmem<BLOCK_N, STAGES>;
-    const bool tma_a = (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0 && (p.Cin % TILE_K) == 0);
+    if (g_force_gather < 0) { const char* e = getenv("SPECB200_FORCE_GATHER"); g_force_gather = (e && e[0] == '1') ? 1 : 0; }
+    int mode = A_GATHER;
+    if (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0 && (p.Cin % TILE_K) == 0) mode = A_TILED;
+    else if ((p.Cin % TILE_K) == 0 && !g_force_gather) mode = A_IM2COL;
     const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
     const int n_tiles = (p.Cout + BLOCK_N - 1) / BLOCK_N;
-    CUtensorMap tmap_a;
-    if (tma_a) {
-        if (!make_tmap_2d(&tmap_a, p.in, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.Cin), TILE_M)) return false;
-    } else {
-        tmap_a = w.tmap_b;     // unused placeholder
+    ConvTcMaps maps;
+    maps.b = w.tmap_b;
+    maps.a = w.tmap_b; maps.out = w.tmap_b; maps.res = w.tmap_b;      // placeholders for unused slots
+    if (mode == A_TILED) {
+        if (!make_tmap_2d(&maps.a, p.in, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.Cin), static_cast<uint64_t>(p.Cin), TILE_M)) return false;
+    } else if (mode == A_IM2COL) {
+        if (!make_tmap_im2col(&maps.a, p)) return false;
     }
-    auto kern_t = conv_tc_kernel<T, BLOCK_N, STAGES, true>;
-    auto kern_g = conv_tc_kernel<T, BLOCK_N, STAGES, false>;
+    if (BLOCK_N >= 64 && (p.Cout & 63) == 0) {
+        if (!make_tmap_2d(&maps.out, p.out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.out_ld), static_cast<uint64_t>(p.out_ld), TILE_M)) return false;
+        if (p.res != nullptr &&
+            !make_tmap_2d(&maps.res, p.res, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.res_ld), static_cast<uint64_t>(p.res_ld), TILE_M)) return false;
+    }
+    auto k0 = conv_tc_kernel<T, BLOCK_N, STAGES, A_TILED>;
+    auto k1 = conv_tc_kernel<T, BLOCK_N, STAGES, A_IM2COL>;
+    auto k2 = conv_tc_kernel<T, BLOCK_N, STAGES, A_GATHER>;
     static bool attr_done = false;
     if (!attr_done) {
-        if (!check_cuda(cudaFuncSetAttribute(kern_t, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
-        if (!check_cuda(cudaFuncSetAttribute(kern_g, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        if (!check_cuda(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        if (!check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        if (!check_cuda(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         attr_done = true;
     }
     const long long grid = static_cast<long long>(m_tiles) * n_tiles;
     if (grid > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return false; }
-    if (tma_a)
-        kern_t<<<static_cast<unsigned>(grid), CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, tmap_a, w.tmap_b, n_tiles);
-    else
-        kern_g<<<static_cast<unsigned>(grid), CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, tmap_a, w.tmap_b, n_tiles);
+    const unsigned g = static_cast<unsigned>(grid);
+    if (mode == A_TILED) k0<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
+    else if (mode == A_IM2COL) k1<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
+    else k2<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
     return check_cuda(cudaGetLastError(), "conv_tc launch");
 }
 

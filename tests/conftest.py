@@ -27,7 +27,7 @@ def pytest_collection_modifyitems(config, items):
 
 
 # ---------------------------------------------------------------- shared builders (tests only)
-def make_pair(backbone='resnet50', seed=0, use_cam=True, use_cam_feats=True):
+def make_pair(backbone='resnet50', seed=0, use_cam=True, use_cam_feats=True, amplify=True):
     """(product HMR, oracle HMR) with identical seeded non-trivial weights, via state_dict transfer."""
     import spec_b200 as sb
     from spec_b200.synthetic import synthetic_smpl_data, synthetic_mean_params, randomize_module_
@@ -37,7 +37,8 @@ def make_pair(backbone='resnet50', seed=0, use_cam=True, use_cam_feats=True):
     ref = om.HMR(backbone, use_cam=use_cam, use_cam_feats=use_cam_feats, smpl_data=smpl, mean_params=mean).eval()
     randomize_module_(ref.backbone, seed)
     from tests.golden.make_golden import amplify_decoders_
-    amplify_decoders_(ref)
+    if amplify:
+        amplify_decoders_(ref)
     prod = sb.HMR(backbone, use_cam=use_cam, use_cam_feats=use_cam_feats, smpl_data=smpl, mean_params=mean).eval()
     missing = prod.load_state_dict(ref.state_dict(), strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys

@@ -219,7 +219,9 @@ def test_lowp_vs_fp32_oracle_deviation_is_small(models):
 # --------------------------------------------------------------------------------------- other backbones
 @pytest.mark.parametrize('backbone', ['hrnet_w32-conv', 'hrnet_w32-interp', 'resnet34'])
 def test_other_backbones_fp32(backbone):
-    hmr, ref = make_pair(backbone, seed=4)
+    # un-normalised random-init HRNet features are large; keep the decoders at their xavier(0.01) scale so the
+    # regressed body stays metre-sized and the absolute 1e-3 vertex bound of the north star is meaningful
+    hmr, ref = make_pair(backbone, seed=4, amplify=False)
     b = synthetic_batch(2, seed=4)
     vfov, pitch, roll = synthetic_camera(2, seed=4)
     R, K, _ = og.cam_params_from_angles(vfov, pitch, roll, b['img_h'], b['img_w'])
@@ -232,9 +234,7 @@ def test_other_backbones_fp32(backbone):
     _assert_close('features', feat, feat_ref, atol=1e-3 * feat_ref.abs().mean().item(), rtol=1e-3)
     got = hmr(b['images'].to(DEV), R.to(DEV), K.to(DEV), b['bbox_scale'].to(DEV), b['bbox_center'].to(DEV),
               b['img_w'].to(DEV), b['img_h'].to(DEV))
-    # random-init HRNet features are large, so the (amplified) head regresses |verts| ~ 70 here: the 1e-3 absolute
-    # bound is kept for metre-scale values and scaled relatively above that
-    _assert_close('smpl_vertices', got['smpl_vertices'], want['smpl_vertices'], atol=1e-3, rtol=1e-4)
+    _assert_close('smpl_vertices', got['smpl_vertices'], want['smpl_vertices'], atol=1e-3)
     _assert_close('pred_cam', got['pred_cam'], want['pred_cam'], atol=1e-5, rtol=1e-5)
 
 
