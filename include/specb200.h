@@ -63,8 +63,8 @@ int specb200_device_check(void);
 
 /* ---- backbone trunk: replaces pare.models.backbone.{resnet,hrnet} called at
  *      /root/reference/camcalib/model.py:73 and /root/reference/spec/models/hmr.py:92 ------------ */
-/* buf_channels[i] = channel stride of activation buffer i; buffer 0 is the NHWC image
- * (4 channels in fp32 mode, 8 in 16-bit modes, zero padded). out_buf = buffer holding the final map. */
+/* buf_channels[i] = channel stride of activation buffer i; buffer 0 is the NHWC image with 4 channels
+ * (RGB + one zero channel). out_buf = buffer holding the final map. */
 int specb200_trunk_create(specb200_trunk_t** out, const specb200_op_t* ops, int32_t n_ops,
                           const int32_t* buf_channels, int32_t n_bufs, int32_t n_wslots, int32_t out_buf,
                           int32_t precision);

@@ -99,7 +99,7 @@ def _bottleneck(P, root, x, pre, inpl, planes, stride, ds):
 
 def _build_resnet(root, P, block, layers):
     exp = 4 if block is _bottleneck else 1
-    x = P.conv(root, 0, 3, 64, 7, 2, 3, 'conv1', 'bn1', True)         # op cin becomes the image padding (4 or 8) at pack time
+    x = P.conv(root, 0, 3, 64, 7, 2, 3, 'conv1', 'bn1', True)         # op cin becomes 4 (NHWC4 image) at pack time
     y = P.op(OP_MAXPOOL, x, P.new(64))
     P.release(x)
     x = y
@@ -303,7 +303,7 @@ class Trunk(nn.Module):
         _lib.require_device()
         self._release()
         prec = _lib.PREC[self.precision]
-        cpad = 4 if self.precision == 'fp32' else 8
+        cpad = 4                      # image stored NHWC4 (RGB + zero channel)
         P = self._program
         buf_ch = list(P.buf_ch)
         buf_ch[0] = cpad
@@ -390,7 +390,7 @@ class Trunk(nn.Module):
                 self.n_output_channels, ms.ctypes.data, torch.cuda.current_stream(images.device).cuda_stream))
         es = 4 if self.precision == 'fp32' else 2
         shapes = {0: (H, W)}
-        rows = [dict(name='images_to_nhwc', type=0, ms=float(ms[0]), flops=0, bytes=B * H * W * (12 + es * (4 if es == 4 else 8)))]
+        rows = [dict(name='images_to_nhwc', type=0, ms=float(ms[0]), flops=0, bytes=B * H * W * (12 + es * 4))]
         for i, o in enumerate(self._program.ops):
             sh = shapes[o['src']]
             r = dict(type=o['type'], ms=float(ms[i + 1]), flops=0)
@@ -398,7 +398,7 @@ class Trunk(nn.Module):
                 ho = (sh[0] + 2 * o['pad'] - o['kh']) // o['stride'] + 1
                 wo = (sh[1] + 2 * o['pad'] - o['kw']) // o['stride'] + 1
                 cin = 3 if o['src'] == 0 else o['cin']
-                cin_s = (4 if es == 4 else 8) if o['src'] == 0 else o['cin']
+                cin_s = 4 if o['src'] == 0 else o['cin']
                 r.update(name=self._program.convs[o['wslot']][0], cin=cin, cout=o['cout'], k=o['kh'], stride=o['stride'],
                          hin=sh[0], hout=ho, flops=2 * B * ho * wo * o['cout'] * cin * o['kh'] * o['kw'],
                          bytes=es * (B * sh[0] * sh[1] * cin_s + B * ho * wo * o['cout'] * (2 if o['src2'] >= 0 else 1)

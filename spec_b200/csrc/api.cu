@@ -162,6 +162,12 @@ extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const
         if (!check_cuda(cudaMemcpy(w.w_f32, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice), "w upload")) return 1;
     } else {
         w.block_n = conv_tc_pick_block_n(cout);
+        if (cin_s == 4) {                           // stem layout: K index = (y*kwp + x)*4 + c
+            w.kwp = 1;
+            while (w.kwp < kw) w.kwp <<= 1;
+            w.K = kh * w.kwp * 4;
+        }
+        const int kw_eff = w.kwp > 0 ? w.kwp : kw;
         w.K_pad = static_cast<int>(align_up(w.K, 64));
         w.cout_pad = static_cast<int>(align_up(cout, w.block_n));
         std::vector<uint16_t> pk(static_cast<size_t>(w.cout_pad) * w.K_pad, 0);
@@ -173,7 +179,7 @@ extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const
                         uint16_t bits;
                         if (t->prec == PREC_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(v); memcpy(&bits, &h, 2); }
                         else { __half h = __float2half_rn(v); memcpy(&bits, &h, 2); }
-                        pk[static_cast<size_t>(o) * w.K_pad + static_cast<size_t>(y * kw + x) * cin_s + c] = bits;
+                        pk[static_cast<size_t>(o) * w.K_pad + static_cast<size_t>(y * kw_eff + x) * cin_s + c] = bits;
                     }
         if (!check_cuda(cudaMalloc(&w.w_tc, pk.size() * 2), "cudaMalloc w_tc")) return 1;
         if (!check_cuda(cudaMemcpy(w.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice), "w upload")) return 1;
@@ -244,7 +250,7 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
                     p.in = buf[o.src]; p.out = buf[o.dst]; p.res = o.src2 >= 0 ? buf[o.src2] : nullptr; p.bias = cw.bias;
                     p.N = nb; p.H = sS.H; p.W = sS.W; p.Cin = o.cin; p.Ho = dS.H; p.Wo = dS.W; p.Cout = o.cout;
                     p.kh = o.kh; p.kw = o.kw; p.stride = o.stride; p.pad = o.pad;
-                    p.K = o.kh * o.kw * o.cin;
+                    p.K = cw.K; p.kwp = cw.kwp;
                     const long long M = static_cast<long long>(nb) * dS.H * dS.W;
                     if (M > 0x7fffffffLL) { set_error("trunk_forward: batch too large"); return 1; }
                     p.M = static_cast<int>(M);

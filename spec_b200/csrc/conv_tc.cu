@@ -12,8 +12,12 @@
 //   A_TILED   1x1 stride-1 convs: A is the plain [M, Cin] matrix -> TMA tiled 2-D load.
 //   A_IM2COL  any conv with Cin % 64 == 0: TMA im2col-mode load straight from the NHWC tensor (the
 //             hardware walks output pixels, applies the filter-tap offset and zero-fills the padding).
-//   A_GATHER  everything else (the 3-channel stem, Cin = 32): warps 0-3 do the im2col in software
-//             with zero-filling cp.async into the same swizzled layout.
+//   A_GATHER  everything else (e.g. Cin = 32): warps 0-3 do the im2col in software with zero-filling
+//             cp.async into the same swizzled layout.
+//   A_STEM    the 3-channel stem conv: the image is stored NHWC with 4 channels (8 bytes / pixel) and K is
+//             ordered (kh, kw padded to a power of two, c4), so the kw pixels of one filter row are
+//             contiguous in memory and are gathered pixel-wise (8-byte cp.async) -- K = 224 -> 256 for
+//             the 7x7 stem instead of 7*7*8 = 392 -> 448 with channel-padded 16-byte chunks.
 // B operand: TMA tiled 2-D load of the [Cout, K] weight matrix.
 //
 //   warps 0-3  (A_GATHER producers, then) epilogue: tcgen05.ld accumulator rows -> +bias (+residual)
@@ -36,7 +40,7 @@ constexpr int TILE_K = 64;                      // 64 x 16-bit = 128 B = one swi
 constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;
 constexpr int GATHER_LAG = 2;                   // cp.async groups kept in flight per producer thread
 constexpr int CONV_TC_THREADS = 192;
-enum { A_TILED = 0, A_IM2COL = 1, A_GATHER = 2 };
+enum { A_TILED = 0, A_IM2COL = 1, A_GATHER = 2, A_STEM = 3 };
 
 template <int BLOCK_N, int STAGES>
 struct ConvTcSmem {
@@ -90,7 +94,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     // ---------------- one-time setup
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + s * 8, A_MODE == A_GATHER ? 5 : 1);   // 4 gather warps + the TMA thread
+            mbar_init(bar_full + s * 8, (A_MODE == A_GATHER || A_MODE == A_STEM) ? 5 : 1);   // 4 gather warps + the TMA thread
             mbar_init(bar_empty + s * 8, 1);
         }
         mbar_init(bar_tmem, 1);
@@ -104,7 +108,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     if (warp == 4) {
         if (lane == 0) {
             tma_prefetch_desc(&maps.b);
-            if (A_MODE != A_GATHER) tma_prefetch_desc(&maps.a);
+            if (A_MODE == A_TILED || A_MODE == A_IM2COL) tma_prefetch_desc(&maps.a);
             if (epi_tma) { tma_prefetch_desc(&maps.out); if (p.res != nullptr) tma_prefetch_desc(&maps.res); }
         }
         __syncwarp();
@@ -121,7 +125,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
         const long long r = static_cast<long long>(m_tile) * TILE_M + t;
         const bool row_ok = r < p.M;
         // ---------------- A producer (software im2col)
-        if constexpr (A_MODE == A_GATHER) {
+        if constexpr (A_MODE == A_GATHER || A_MODE == A_STEM) {
             const T* __restrict__ in = static_cast<const T*>(p.in);
             int n = 0, oh = 0, ow = 0;
             if (row_ok) {
@@ -142,7 +146,20 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
                 const int it = kb / STAGES;
                 mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
                 const uint32_t dst = a_base + s * A_STAGE_BYTES + row_off;
-                if (uniform_tap) {
+                if constexpr (A_MODE == A_STEM) {
+                    const int kw_mask = p.kwp - 1;
+                    const int kw_shift = 31 - __clz(p.kwp);
+#pragma unroll
+                    for (int pp = 0; pp < 16; ++pp) {             // 16 pixels (8 B each) per 128-byte K slice
+                        const int idx = kb * 16 + pp;
+                        const int khi = idx >> kw_shift, kwi = idx & kw_mask;
+                        const int ih = ih0 + khi, iw = iw0 + kwi;
+                        const bool ok = row_ok && khi < p.kh && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
+                                        static_cast<unsigned>(iw) < static_cast<unsigned>(p.W);
+                        const T* src = ok ? base + (static_cast<size_t>(ih) * p.W + iw) * 4 : in;
+                        cp_async8(dst + (((pp >> 1) ^ sw) << 4) + (pp & 1) * 8, src, ok);
+                    }
+                } else if (uniform_tap) {
                     const int k0 = kb * TILE_K;
                     const int tap = k0 / p.Cin;
                     const int c0 = k0 - tap * p.Cin;
@@ -288,7 +305,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     } else if (warp == 4) {
         // ---------------- TMA producer
         if (lane == 0) {
-            constexpr uint32_t tx_bytes = L::B_STAGE_BYTES + (A_MODE != A_GATHER ? A_STAGE_BYTES : 0);
+            constexpr uint32_t tx_bytes = L::B_STAGE_BYTES + ((A_MODE == A_TILED || A_MODE == A_IM2COL) ? A_STAGE_BYTES : 0);
             int pw = 0, ph = 0, pn = 0;                           // im2col base pixel of the tile's first row
             if constexpr (A_MODE == A_IM2COL) {
                 const long long r0 = static_cast<long long>(m_tile) * TILE_M;
@@ -432,7 +449,8 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
     using L = ConvTcSmem<BLOCK_N, STAGES>;
     if (g_force_gather < 0) { const char* e = getenv("SPECB200_FORCE_GATHER"); g_force_gather = (e && e[0] == '1') ? 1 : 0; }
     int mode = A_GATHER;
-    if (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0 && (p.Cin % TILE_K) == 0) mode = A_TILED;
+    if (w.kwp > 0) mode = A_STEM;
+    else if (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0 && (p.Cin % TILE_K) == 0) mode = A_TILED;
     else if ((p.Cin % TILE_K) == 0 && !g_force_gather) mode = A_IM2COL;
     const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
     const int n_tiles = (p.Cout + BLOCK_N - 1) / BLOCK_N;
@@ -452,11 +470,13 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
     auto k0 = conv_tc_kernel<T, BLOCK_N, STAGES, A_TILED>;
     auto k1 = conv_tc_kernel<T, BLOCK_N, STAGES, A_IM2COL>;
     auto k2 = conv_tc_kernel<T, BLOCK_N, STAGES, A_GATHER>;
+    auto k3 = conv_tc_kernel<T, BLOCK_N, STAGES, A_STEM>;
     static bool attr_done = false;
     if (!attr_done) {
         if (!check_cuda(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         if (!check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         if (!check_cuda(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        if (!check_cuda(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         attr_done = true;
     }
     const long long grid = static_cast<long long>(m_tiles) * n_tiles;
@@ -464,6 +484,7 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
     const unsigned g = static_cast<unsigned>(grid);
     if (mode == A_TILED) k0<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
     else if (mode == A_IM2COL) k1<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
+    else if (mode == A_STEM) k3<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
     else k2<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
     return check_cuda(cudaGetLastError(), "conv_tc launch");
 }
@@ -480,7 +501,7 @@ static bool launch_dt(const ConvParams& p, const ConvWeights& w, cudaStream_t s)
 
 bool conv_tc_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s) {
     if (!w.has_tmap) { set_error("conv_tc: weights not packed"); return false; }
-    if ((p.Cin % 8) != 0 || (p.Cout % 8) != 0 || (p.out_ld % 8) != 0 || (p.out_coff % 8) != 0 ||
+    if (((p.Cin % 8) != 0 && w.kwp == 0) || (w.kwp > 0 && p.Cin != 4) || (p.Cout % 8) != 0 || (p.out_ld % 8) != 0 || (p.out_coff % 8) != 0 ||
         (p.res != nullptr && (p.res_ld % 8) != 0)) {
         set_error("conv_tc: channel counts / strides must be multiples of 8");
         return false;

@@ -42,21 +42,25 @@ static inline unsigned nblk(long long n, int t) { return static_cast<unsigned>((
 // ------------------------------------------------------------------ images NCHW f32 -> NHWC(cpad)
 template <typename T>
 __global__ void images_to_nhwc_kernel(const float* __restrict__ img, T* __restrict__ out, long long npix, int HW) {
-    constexpr int CP = V16<T>::N;                  // 4 (fp32) or 8 (16-bit) channels, zero padded
+    // NHWC with 4 channels (RGB + one zero): 16 B / pixel in fp32, 8 B / pixel in the 16-bit modes
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     const long long n = i / HW;
     const int hw = static_cast<int>(i - n * HW);
     const float* src = img + n * 3 * HW + hw;
-    float f[CP];
-#pragma unroll
-    for (int c = 0; c < CP; ++c) f[c] = 0.f;
-    f[0] = src[0]; f[1] = src[HW]; f[2] = src[2 * static_cast<size_t>(HW)];
-    V16<T>::store(out + i * CP, f);
+    const float r = src[0], g = src[HW], b = src[2 * static_cast<size_t>(HW)];
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(out + i * 4) = make_float4(r, g, b, 0.f);
+    } else {
+        uint2 v;
+        v.x = DT<T>::pack2(r, g);
+        v.y = DT<T>::pack2(b, 0.f);
+        *reinterpret_cast<uint2*>(out + i * 4) = v;
+    }
 }
 bool images_to_nhwc_launch(const float* img, void* out, int N, int H, int W, int cpad, int prec, cudaStream_t s) {
     const long long npix = static_cast<long long>(N) * H * W;
-    if (cpad != (prec == PREC_F32 ? 4 : 8)) { set_error("images_to_nhwc: cpad mismatch"); return false; }
+    if (cpad != 4) { set_error("images_to_nhwc: the image buffer must have 4 channels"); return false; }
     SB_DISPATCH_PREC(prec, (images_to_nhwc_kernel<T><<<nblk(npix, 256), 256, 0, s>>>(img, static_cast<T*>(out), npix, H * W)));
     return check_cuda(cudaGetLastError(), "images_to_nhwc");
 }

@@ -18,7 +18,8 @@ struct ConvParams {
     int N, H, W, Cin;
     int Ho, Wo, Cout;
     int kh, kw, stride, pad;
-    int K;               // kh*kw*Cin
+    int kwp;             // stem layout only: kw padded to a power of two (K index = (kh*kwp + kw)*4 + c)
+    int K;               // GEMM K (kh*kw*Cin; kh*kwp*4 for the stem layout)
     int M;               // N*Ho*Wo
     int out_ld, out_coff, res_ld;
     int relu;
@@ -28,6 +29,7 @@ struct ConvParams {
 struct ConvWeights {
     int cout = 0, cin = 0, kh = 0, kw = 0;
     int K = 0, K_pad = 0, cout_pad = 0, block_n = 0;
+    int kwp = 0;               // > 0: stem layout (Cin stored = 4, kw padded to kwp)
     void* w_tc = nullptr;      // [cout_pad][K_pad] 16-bit, K-major (tcgen05 path)
     float* w_f32 = nullptr;    // [K][cout] fp32 (SIMT parity path)
     float* bias = nullptr;     // [cout]
