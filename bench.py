@@ -96,13 +96,36 @@ def build_oracle(backbone):
     return cc, hmr
 
 
+def pick_cpu_threads(cc, sample):
+    """All the host threads the oracle can USE: eager PyTorch convs stop scaling (and collapse under
+    oversubscription / cgroup quotas) well before 128 threads, so calibrate on one CamCalib forward and keep
+    the fastest count among {8,16,32,64,all}."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail}) or [avail]
+    x = torch.randn(sample, 3, 224, 224)
+    best, best_t = cands[-1], float('inf')
+    for c in cands:
+        torch.set_num_threads(c)
+        with torch.no_grad():
+            cc(x)
+            t0 = time.perf_counter()
+            cc(x)
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def time_oracle(backbone, sample, steps, warmup):
-    """Oracle (CPU restatement of the reference path) on all host cores; returns (images/s, ms per sample step)."""
+    """Oracle (CPU restatement of the reference path) on the host cores; returns (images/s, ms per sample step, threads)."""
     from oracle.models import spec_full_forward
     from spec_b200.synthetic import synthetic_batch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     cc, hmr = build_oracle(backbone)
+    cores = pick_cpu_threads(cc, sample)
+    torch.set_num_threads(cores)
     b = synthetic_batch(sample, 0)
     args = (b['images'], b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'])
     for _ in range(warmup):
@@ -170,8 +193,13 @@ def run_ours(a):
         return rec
 
     def timed(fn, steps, warmup):
-        for _ in range(warmup):
+        t_w = time.perf_counter()
+        n_w = 0
+        while n_w < warmup or time.perf_counter() - t_w < 0.4:     # >= W steps AND ~0.4 s so the clocks have ramped
             fn()
+            n_w += 1
+            if n_w % 4 == 0:
+                torch.cuda.synchronize(dev)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -190,6 +218,16 @@ def run_ours(a):
         return ms.item()
 
     # ---- value: inputs resident in HBM
+    if a.profile_range:
+        for _ in range(a.warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        for _ in range(a.steps):
+            step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return None
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -199,24 +237,72 @@ def run_ours(a):
     value = world * B * a.steps / (total_ms * 1e-3)
     launches_per_step = pipe.launches_per_step()
 
-    # ---- e2e: public API with HOST (pinned) inputs, H2D + D2H inside the timed region
+    # ---- e2e: public API with HOST (pinned) inputs; every step copies its inputs H2D and its results D2H inside the
+    # timed region.  The copies ride on side streams (double-buffered staging) so they overlap the previous /
+    # next step's kernels -- what a serving loop built on the public API does.
     host = {k: v.cpu().pin_memory() for k, v in b.items()}
-    host_rec = torch.empty(B, RECORD_FLOATS, dtype=torch.float32).pin_memory()
-    dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    keys = ('images', 'bbox_scale', 'bbox_center', 'img_w', 'img_h')
+    staging = [{k: torch.empty_like(host[k], device=dev) for k in keys} for _ in range(2)]
+    rec_dev = [torch.empty(B, RECORD_FLOATS, dtype=torch.float32, device=dev) for _ in range(2)]
+    host_rec = [torch.empty(B, RECORD_FLOATS, dtype=torch.float32).pin_memory() for _ in range(2)]
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
 
-    def e2e_step():
-        for k in dbuf:
-            dbuf[k].copy_(host[k], non_blocking=True)
-        rec = pipe.forward_packed(dbuf['images'], dbuf['bbox_scale'], dbuf['bbox_center'], dbuf['img_w'], dbuf['img_h'])
-        if world > 1:
-            rec = sb.all_gather_records(rec)[rank * B:(rank + 1) * B]
-        host_rec.copy_(rec, non_blocking=True)
+    def e2e_run(steps):
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        ev_used = [None, None]
+        ev_d2h = [None, None]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    e2e_steps = max(3, min(a.steps, 10))
-    e2e_ms = timed(e2e_step, e2e_steps, 3)
+        def issue_h2d(i):
+            sl = i % 2
+            with torch.cuda.stream(s_h2d):
+                if ev_used[sl] is not None:
+                    s_h2d.wait_event(ev_used[sl])                 # staging slot consumed by step i-2
+                for k in keys:
+                    staging[sl][k].copy_(host[k], non_blocking=True)
+                ev_h2d[sl].record(s_h2d)
+
+        with torch.cuda.stream(s_h2d):
+            e0.record(s_h2d)
+        issue_h2d(0)
+        for i in range(steps):
+            sl = i % 2
+            if i + 1 < steps:
+                issue_h2d(i + 1)
+            main.wait_event(ev_h2d[sl])
+            if ev_d2h[sl] is not None:
+                main.wait_event(ev_d2h[sl])                       # rec_dev[sl] read back by step i-2
+            st = staging[sl]
+            rec = pipe.forward_packed(st['images'], st['bbox_scale'], st['bbox_center'], st['img_w'], st['img_h'])
+            if world > 1:
+                rec = sb.all_gather_records(rec)[rank * B:(rank + 1) * B]
+            rec_dev[sl].copy_(rec, non_blocking=True)
+            ev_used[sl] = torch.cuda.Event()
+            ev_used[sl].record(main)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_used[sl])
+                host_rec[sl].copy_(rec_dev[sl], non_blocking=True)
+                ev_d2h[sl] = torch.cuda.Event()
+                ev_d2h[sl].record(s_d2h)
+        with torch.cuda.stream(s_d2h):
+            e1.record(s_d2h)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1)
+
+    e2e_steps = max(4, min(a.steps, 20))
+    e2e_run(8)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e2e_ms_t = torch.tensor([e2e_run(e2e_steps)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(e2e_ms_t, op=dist.ReduceOp.MAX)
+    e2e_ms = e2e_ms_t.item()
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = host_rec.numel() * 4
+    d2h = host_rec[0].numel() * 4
 
     out = None
     if rank == 0:
@@ -246,7 +332,8 @@ def run_ours(a):
                        'l2': 'inputs 154 MB/step/GPU > 126 MB L2, no explicit flush (weights stay L2-resident as in steady-state serving)',
                        'parallelism': f'dp{world} (batch shard + one all-gather of 85,176 B/image records)' if world > 1 else 'single GPU'},
             'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / e2e_steps},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / e2e_steps,
+                    'steps': e2e_steps, 'how': 'pinned host inputs -> H2D -> SPECPipeline.forward_packed -> D2H of the packed records; copies on side streams, double-buffered'},
             'gpu_launches': int(launches_per_step * a.steps),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
                          'frac': achieved / peaks['tf_sustained'], 'traffic': None,
@@ -276,6 +363,7 @@ def main():
     ap.add_argument('--chunk', type=int, default=int(os.environ.get('SPECB200_CHUNK', '0')))
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-range', action='store_true', help='only run the steps inside cudaProfilerStart/Stop (for ncu --profile-from-start off)')
     ap.add_argument('--cpu-sample', type=int, default=16, help='images per CPU-oracle step (bounded sample)')
     a = ap.parse_args()
     if a.warmup < 3:

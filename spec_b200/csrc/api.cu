@@ -41,6 +41,7 @@ struct specb200_trunk {
     int out_buf = 0;
     int prec = PREC_BF16;
     int chunk = 0;
+    int stem7_slot = -1;             // >= 0: op 0 is the ResNet 7x7/2 stem and runs in conv_stem7_kernel (reads the NCHW image)
     int64_t last_launches = 0;
     std::vector<cudaEvent_t> prof_ev;        // non-empty only inside specb200_trunk_profile
     size_t prof_n = 0;
@@ -129,6 +130,14 @@ extern "C" int specb200_trunk_create(specb200_trunk_t** out, const specb200_op_t
             t->wslot_cin[o.wslot] = o.cin;
         }
     }
+    {   // ResNet stem: dedicated kernel when op 0 is conv 7x7/2 pad 3 -> 64 (+ReLU) on the image and nothing else reads it
+        const specb200_op_t& o = t->ops[0];
+        bool ok = t->prec != PREC_F32 && o.type == SPECB200_OP_CONV && o.src == 0 && o.kh == 7 && o.kw == 7 && o.stride == 2 &&
+                  o.pad == 3 && o.cout == 64 && o.relu && o.src2 < 0 && o.dst_coff == 0 && t->buf_ch[o.dst] == 64;
+        for (size_t i = 1; i < t->ops.size() && ok; ++i) ok = t->ops[i].src != 0 && t->ops[i].src2 != 0;
+        const char* e = getenv("SPECB200_NO_STEM7");
+        if (ok && !(e && e[0] == '1')) t->stem7_slot = o.wslot;
+    }
     *out = t;
     return 0;
 }
@@ -160,6 +169,23 @@ extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const
                         pk[(static_cast<size_t>(y * kw + x) * cin_s + c) * cout + o] = w_host[((static_cast<size_t>(o) * cin + c) * kh + y) * kw + x];
         if (!check_cuda(cudaMalloc(&w.w_f32, pk.size() * sizeof(float)), "cudaMalloc w_f32")) return 1;
         if (!check_cuda(cudaMemcpy(w.w_f32, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice), "w upload")) return 1;
+    } else if (wslot == t->stem7_slot) {
+        if (cin != 3 || cout != 64 || kh != 7 || kw != 7) { set_error("set_conv: stem weights must be [64][3][7][7]"); return 1; }
+        w.stem7 = true; w.block_n = 64; w.cout_pad = 64; w.K = 168; w.K_pad = 192;
+        std::vector<uint16_t> pk(static_cast<size_t>(64) * 192, 0);
+        for (int o = 0; o < 64; ++o)
+            for (int c = 0; c < 3; ++c)
+                for (int y = 0; y < 7; ++y)
+                    for (int x = 0; x < 7; ++x) {
+                        const float v = w_host[((static_cast<size_t>(o) * 3 + c) * 7 + y) * 7 + x];
+                        uint16_t bits;
+                        if (t->prec == PREC_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(v); memcpy(&bits, &h, 2); }
+                        else { __half h = __float2half_rn(v); memcpy(&bits, &h, 2); }
+                        pk[static_cast<size_t>(o) * 192 + (c * 7 + y) * 8 + x] = bits;
+                    }
+        if (!check_cuda(cudaMalloc(&w.w_tc, pk.size() * 2), "cudaMalloc w_tc")) return 1;
+        if (!check_cuda(cudaMemcpy(w.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice), "w upload")) return 1;
+        if (!conv_tc_make_weight_tmap(w)) return 1;
     } else {
         w.block_n = conv_tc_pick_block_n(cout);
         if (cin_s == 4) {                           // stem layout: K index = (y*kwp + x)*4 + c
@@ -235,12 +261,22 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
     for (int b0 = 0; b0 < batch; b0 += eb) {
         const int nb = std::min(eb, batch - b0);
         mark();
-        if (!images_to_nhwc_launch(images + static_cast<size_t>(b0) * 3 * h * w, buf[0], nb, h, w, t->buf_ch[0], t->prec, s)) return 1;
-        ++launches;
+        if (t->stem7_slot < 0) {
+            if (!images_to_nhwc_launch(images + static_cast<size_t>(b0) * 3 * h * w, buf[0], nb, h, w, t->buf_ch[0], t->prec, s)) return 1;
+            ++launches;
+        }
         mark();
         for (size_t i = 0; i < t->ops.size(); ++i) {
             const specb200_op_t& o = t->ops[i];
             const BufShape sS = t->op_src[i], dS = t->op_dst[i];
+            if (i == 0 && t->stem7_slot >= 0) {
+                const ConvWeights& cw = t->w[o.wslot];
+                if (cw.bias == nullptr) { set_error("trunk_forward: stem weights not set"); return 1; }
+                if (!conv_stem7_launch(images + static_cast<size_t>(b0) * 3 * h * w, buf[o.dst], cw, nb, sS.H, sS.W, dS.H, dS.W, t->prec, s)) return 1;
+                ++launches;
+                mark();
+                continue;
+            }
             switch (o.type) {
                 case SPECB200_OP_CONV: {
                     const ConvWeights& cw = t->w[o.wslot];

@@ -1,0 +1,206 @@
+// ResNet stem on the tensor cores: conv 7x7 / stride 2 / pad 3 (3 -> 64) + folded BN + ReLU, reading the
+// fp32 NCHW image directly and writing NHWC 16-bit (replaces the first cuDNN conv + BN + ReLU of
+// pare's resnet trunk; call sites /root/reference/camcalib/model.py:73, /root/reference/spec/models/hmr.py:92).
+//
+// With Cin = 3 the generic implicit-GEMM paths spend their time producing the A operand (K = 147 is
+// neither TMA-im2col-able nor 16-byte granular).  This kernel builds A from an on-chip input patch instead:
+//   tile = 8 x 16 output pixels (one 128-row UMMA tile) of one image
+//   1. all threads load the (2*8+5) x (2*16+5) x 3 input patch (fp32 NCHW, rounded to 16 bit) into smem;
+//   2. each A row (output pixel) is assembled from the patch: K is ordered (c, kh, kw padded to 8), so one
+//      16-byte chunk = 8 consecutive patch elements of one (c, kh) filter row; K = 21 chunks -> 192;
+//   3. one thread issues 12 tcgen05.mma (M=128, N=64, K=16) against the weight matrix that stays resident in
+//      smem (24 KB, TMA-loaded once per CTA);
+//   4. epilogue: tcgen05.ld -> +bias -> ReLU -> 16 bit -> swizzled smem -> coalesced 16-byte global stores.
+// The CTA is sequential per tile; two to three co-resident CTAs per SM (93 KB smem each) overlap the phases.
+#include "common.cuh"
+#include "internal.h"
+
+namespace sb {
+
+constexpr int ST_TH = 8, ST_TW = 16;                 // output tile
+constexpr int ST_PR = 2 * ST_TH + 5;                 // 21 patch rows
+constexpr int ST_PC = 2 * ST_TW + 5;                 // 37 patch cols
+constexpr int ST_PP = 40;                            // patch row pitch (elements)
+constexpr int ST_KB = 3;                             // K = 192 = 3 x 64
+constexpr int ST_A_BYTES = ST_KB * 128 * 128;        // 49152
+constexpr int ST_B_BYTES = ST_KB * 64 * 128;         // 24576
+constexpr int ST_STAGE_BYTES = 128 * 128;            // 16384
+constexpr int ST_PATCH_BYTES = 3 * ST_PR * ST_PP * 2;    // 5040
+constexpr int ST_OFF_B = ST_A_BYTES;
+constexpr int ST_OFF_STAGE = ST_OFF_B + ST_B_BYTES;
+constexpr int ST_OFF_PATCH = ST_OFF_STAGE + ST_STAGE_BYTES;
+constexpr int ST_OFF_BIAS = ST_OFF_PATCH + 5120;
+constexpr int ST_OFF_BAR = ST_OFF_BIAS + 256;
+constexpr int ST_DYN_BYTES = ST_OFF_BAR + 64 + 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_stem7_kernel(const float* __restrict__ img, T* __restrict__ out, const float* __restrict__ bias,
+                  const __grid_constant__ CUtensorMap tmap_b, int N, int H, int W, int Ho, int Wo,
+                  int tiles_h, int tiles_w, int total_tiles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t a_base = sbase;
+    const uint32_t b_base = sbase + ST_OFF_B;
+    const uint32_t st_base = sbase + ST_OFF_STAGE;
+    T* patch = reinterpret_cast<T*>(sgen + ST_OFF_PATCH);
+    float* sbias = reinterpret_cast<float*>(sgen + ST_OFF_BIAS);
+    const uint32_t bar_b = sbase + ST_OFF_BAR;
+    const uint32_t bar_mma = bar_b + 8;
+    volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sgen + ST_OFF_BAR + 16);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        mbar_init(bar_mma, 1);
+        mbar_fence_init();
+    }
+    if (tid < 64) sbias[tid] = bias[tid];
+    for (int i = tid; i < 3 * ST_PR * ST_PP; i += 256) patch[i] = DT<T>::from_f(0.f);   // pad columns stay zero
+    if (warp == 1) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), 64);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_ptr_s;
+    if (tid == 0) {                                      // weights: resident for the whole kernel
+        tma_prefetch_desc(&tmap_b);
+        mbar_arrive_expect_tx(bar_b, ST_B_BYTES);
+        for (int kb = 0; kb < ST_KB; ++kb) tma_load_2d(b_base + kb * 8192, &tmap_b, bar_b, kb * 64, 0);
+    }
+    mbar_wait(bar_b, 0);
+
+    const size_t plane = static_cast<size_t>(H) * W;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int tw = tile % tiles_w;
+        const int th = (tile / tiles_w) % tiles_h;
+        const int n = tile / (tiles_w * tiles_h);
+        const int oh0 = th * ST_TH, ow0 = tw * ST_TW;
+        const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
+        // ---- 1. input patch -> smem (16 bit)
+        const float* src = img + static_cast<size_t>(n) * 3 * plane;
+        for (int i = tid; i < 3 * ST_PR * ST_PC; i += 256) {
+            const int c = i / (ST_PR * ST_PC);
+            const int rem = i - c * (ST_PR * ST_PC);
+            const int r = rem / ST_PC, col = rem - r * ST_PC;
+            const int ih = ih0 + r, iw = iw0 + col;
+            float v = 0.f;
+            if (static_cast<unsigned>(ih) < static_cast<unsigned>(H) && static_cast<unsigned>(iw) < static_cast<unsigned>(W))
+                v = __ldg(src + c * plane + static_cast<size_t>(ih) * W + iw);
+            patch[(c * ST_PR + r) * ST_PP + col] = DT<T>::from_f(v);
+        }
+        __syncthreads();
+        // ---- 2. A rows from the patch: thread pair (t, half) builds 12 of the 24 chunks of row t
+        {
+            const int t = tid & 127, half = tid >> 7;
+            const int lr = t >> 4, lc = t & 15;
+            const uint32_t sw = static_cast<uint32_t>(t) & 7u;
+#pragma unroll
+            for (int jj = 0; jj < 12; ++jj) {
+                const int j = half * 12 + jj;
+                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                if (j < 21) {
+                    const int c = j / 7, kh = j - c * 7;
+                    const uint32_t* s = reinterpret_cast<const uint32_t*>(patch + (c * ST_PR + 2 * lr + kh) * ST_PP + 2 * lc);
+                    w0 = s[0]; w1 = s[1]; w2 = s[2]; w3 = s[3];
+                }
+                const uint32_t dst = a_base + (j >> 3) * 16384 + static_cast<uint32_t>(t) * 128u + (((j & 7) ^ sw) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- 3. MMA
+        if (tid == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = umma_idesc_f16(DT<T>::umma_fmt, 128, 64);
+#pragma unroll
+            for (int kb = 0; kb < ST_KB; ++kb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tmem_acc, umma_desc_sw128(a_base + kb * 16384 + k * 32), umma_desc_sw128(b_base + kb * 8192 + k * 32),
+                             idesc, static_cast<uint32_t>((kb | k) != 0));
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, it & 1);
+        tc_fence_after();
+        // ---- 4. epilogue: warp w -> TMEM lane quarter (w & 3), column half (w >> 2)
+        {
+            const int row = (warp & 3) * 32 + lane;
+            const int ch = warp >> 2;
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>((warp & 3) * 32) << 16) + ch * 32, v);
+            tmem_ld_wait();
+            const uint32_t sw = static_cast<uint32_t>(row) & 7u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[q * 8 + e]) + sbias[ch * 32 + q * 8 + e], 0.f);
+                const uint32_t dst = st_base + static_cast<uint32_t>(row) * 128u + (((ch * 4 + q) ^ sw) << 4);
+                const uint32_t o0 = DT<T>::pack2(f[0], f[1]), o1 = DT<T>::pack2(f[2], f[3]);
+                const uint32_t o2 = DT<T>::pack2(f[4], f[5]), o3 = DT<T>::pack2(f[6], f[7]);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- 5. coalesced store of the 128 x 64 tile (16 B per thread, 4 iterations)
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep) {
+            const int i = rep * 256 + tid;
+            const int row = i >> 3, chk = i & 7;
+            const int oh = oh0 + (row >> 4), ow = ow0 + (row & 15);
+            if (oh < Ho && ow < Wo) {
+                uint4 val;
+                const uint32_t srca = st_base + static_cast<uint32_t>(row) * 128u + ((chk ^ (row & 7)) << 4);
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(srca));
+                *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * Ho + oh) * Wo + ow) * 64 + chk * 8) = val;
+            }
+        }
+        // the next iteration's two __syncthreads (after patch load / after A build) order the smem reuse
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_acc, 64);
+    }
+}
+
+bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N, int H, int W, int Ho, int Wo, int prec,
+                       cudaStream_t s) {
+    if (!w.has_tmap || !w.stem7) { set_error("conv_stem7: weights not packed for the stem kernel"); return false; }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!check_cuda(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev), "sm count")) return false;
+    }
+    const int tiles_h = (Ho + ST_TH - 1) / ST_TH, tiles_w = (Wo + ST_TW - 1) / ST_TW;
+    const long long total = static_cast<long long>(N) * tiles_h * tiles_w;
+    if (total > 0x7fffffffLL) { set_error("conv_stem7: too many tiles"); return false; }
+    const unsigned grid = static_cast<unsigned>(total < 2LL * num_sms ? total : 2LL * num_sms);
+    static bool attr = false;
+    if (!attr) {
+        if (!check_cuda(cudaFuncSetAttribute(conv_stem7_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_BYTES), "stem attr")) return false;
+        if (!check_cuda(cudaFuncSetAttribute(conv_stem7_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_BYTES), "stem attr")) return false;
+        attr = true;
+    }
+    if (prec == PREC_BF16)
+        conv_stem7_kernel<__nv_bfloat16><<<grid, 256, ST_DYN_BYTES, s>>>(img, static_cast<__nv_bfloat16*>(out), w.bias, w.tmap_b, N, H, W, Ho, Wo, tiles_h, tiles_w, static_cast<int>(total));
+    else if (prec == PREC_F16)
+        conv_stem7_kernel<__half><<<grid, 256, ST_DYN_BYTES, s>>>(img, static_cast<__half*>(out), w.bias, w.tmap_b, N, H, W, Ho, Wo, tiles_h, tiles_w, static_cast<int>(total));
+    else { set_error("conv_stem7: 16-bit precisions only"); return false; }
+    return check_cuda(cudaGetLastError(), "conv_stem7 launch");
+}
+
+}  // namespace sb

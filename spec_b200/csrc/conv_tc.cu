@@ -367,6 +367,233 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------ persistent kernel
+// One CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x, Cout tiles fastest so CTAs running
+// concurrently share the A tile in L2).  Compared with the one-tile kernel above it
+//   * pays barrier init / TMEM alloc / descriptor fetch once per SM instead of once per tile,
+//   * double-buffers the accumulator in TMEM (2 x BLOCK_N columns): the MMA warp starts tile i+1 while the
+//     epilogue warps drain tile i,
+//   * double-buffers the epilogue staging tile: the residual of tile i+1 is TMA-prefetched while tile i is being
+//     combined, and the TMA store of tile i overlaps the main loop of tile i+1.
+// A comes by TMA (tiled or im2col), so there are no gather warps: warp 0 = TMA producer, warp 1 = MMA issuer,
+// warp 2 = TMEM owner, warps 4-11 = epilogue (two groups of four warps, each group owns half of the columns:
+// short-K layers are bound by the epilogue's conversion work, so it gets 8 warps).
+constexpr int CONV_TCP_THREADS = 384;          // warps 0-3: TMA / MMA / TMEM / idle; warps 4-11: epilogue (2 column halves)
+
+template <int BLOCK_N, int STAGES>
+struct ConvTcpSmem {
+    static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
+    static constexpr int EPI_BYTES = TILE_M * BLOCK_N * 2;
+    static constexpr int A_OFF = 0;
+    static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+    static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+    static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BYTES;        // full[S], empty[S], tfull[2], tempty[2], rfull[2]
+    static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 6) * 8;
+    static constexpr int BIAS_OFF = (TMEMPTR_OFF + 8 + 15) / 16 * 16;
+    static constexpr int MAX_COUT = 2048;
+    static constexpr int TOTAL = BIAS_OFF + MAX_COUT * 4;
+    static constexpr int DYN_BYTES = TOTAL + 1024;
+    static_assert(DYN_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+};
+
+template <typename T, int BLOCK_N, int STAGES, int A_MODE>
+__global__ void __launch_bounds__(CONV_TCP_THREADS, 1)
+conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int n_tiles, int total_tiles)
+{
+    static_assert(A_MODE == A_TILED || A_MODE == A_IM2COL, "persistent kernel is TMA-fed");
+    using L = ConvTcpSmem<BLOCK_N, STAGES>;
+    constexpr int TMEM_COLS = 2 * BLOCK_N;
+    constexpr int BOXES = BLOCK_N / 64;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t a_base = sbase + L::A_OFF;
+    const uint32_t b_base = sbase + L::B_OFF;
+    const uint32_t e_base = sbase + L::EPI_OFF;
+    const uint32_t bar_full = sbase + L::BAR_OFF;
+    const uint32_t bar_empty = bar_full + STAGES * 8;
+    const uint32_t bar_tfull = bar_empty + STAGES * 8;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    const uint32_t bar_rfull = bar_tempty + 16;
+    volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sgen + L::TMEMPTR_OFF);
+    float* sbias = reinterpret_cast<float*>(sgen + L::BIAS_OFF);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = (p.K + TILE_K - 1) / TILE_K;
+    const bool has_res = p.res != nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + a * 8, 1); mbar_init(bar_tempty + a * 8, 8); mbar_init(bar_rfull + a * 8, 1); }
+        mbar_fence_init();
+    }
+    for (int c = threadIdx.x; c < p.Cout; c += CONV_TCP_THREADS) sbias[c] = p.bias[c];
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.a); tma_prefetch_desc(&maps.b); tma_prefetch_desc(&maps.out);
+        if (has_res) tma_prefetch_desc(&maps.res);
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0) {
+        // ================= TMA producer
+        if (lane == 0) {
+            constexpr uint32_t tx_bytes = L::B_STAGE_BYTES + A_STAGE_BYTES;
+            const int hw = p.Ho * p.Wo;
+            uint32_t kc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+                const int n0 = n_tile * BLOCK_N;
+                int pw = 0, ph = 0, pn = 0;
+                if constexpr (A_MODE == A_IM2COL) {
+                    const long long r0 = static_cast<long long>(m_tile) * TILE_M;
+                    pn = static_cast<int>(r0 / hw);
+                    const int rem = static_cast<int>(r0 - static_cast<long long>(pn) * hw);
+                    const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+                    pw = ow * p.stride - p.pad;
+                    ph = oh * p.stride - p.pad;
+                }
+                for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+                    const uint32_t s = kc % STAGES, it = kc / STAGES;
+                    mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
+                    mbar_arrive_expect_tx(bar_full + s * 8, tx_bytes);
+                    tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
+                    if constexpr (A_MODE == A_TILED) {
+                        tma_load_2d(a_base + s * A_STAGE_BYTES, &maps.a, bar_full + s * 8, kb * TILE_K, m_tile * TILE_M);
+                    } else {
+                        const int k0 = kb * TILE_K;
+                        const int tap = k0 / p.Cin;
+                        const int c0 = k0 - tap * p.Cin;
+                        const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+                        tma_load_im2col_4d(a_base + s * A_STAGE_BYTES, &maps.a, bar_full + s * 8, c0, pw, ph, pn,
+                                           static_cast<uint16_t>(kwi), static_cast<uint16_t>(khi));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(DT<T>::umma_fmt, TILE_M, BLOCK_N);
+            uint32_t kc = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+                const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
+                mbar_wait(bar_tempty + a * 8, aph ^ 1);            // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + a * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+                    const uint32_t s = kc % STAGES, it = kc / STAGES;
+                    mbar_wait(bar_full + s * 8, it & 1);
+                    tc_fence_after();
+                    const uint32_t a_s = a_base + s * A_STAGE_BYTES;
+                    const uint32_t b_s = b_base + s * L::B_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TILE_K / 16; ++k)
+                        umma_f16(tmem_acc, umma_desc_sw128(a_s + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
+                                 static_cast<uint32_t>((kb | k) != 0));
+                    umma_commit(bar_empty + s * 8);
+                }
+                umma_commit(bar_tfull + a * 8);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ================= epilogue (256 threads; row t == TMEM lane t; column half `grp`)
+        const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int grp = (warp - 4) >> 2;                           // 0: columns [0, N/2), 1: [N/2, N)
+        const int t = q4 * 32 + lane;
+        const bool leader = (warp == 4 && lane == 0);
+        const uint32_t sw = static_cast<uint32_t>(t) & 7u;
+        auto issue_res = [&](int tile, uint32_t a) {
+            const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+            mbar_arrive_expect_tx(bar_rfull + a * 8, L::EPI_BYTES);
+#pragma unroll
+            for (int bx = 0; bx < BOXES; ++bx)
+                tma_load_2d(e_base + a * L::EPI_BYTES + bx * (TILE_M * 128), &maps.res, bar_rfull + a * 8,
+                            n_tile * BLOCK_N + bx * 64, m_tile * TILE_M);
+        };
+        if (leader && has_res && static_cast<int>(blockIdx.x) < total_tiles) issue_res(blockIdx.x, 0);
+        uint32_t tc = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+            const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
+            const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+            const int n0 = n_tile * BLOCK_N;
+            if (leader) {
+                tma_store_wait_read0();                            // store of tile tc-1 has finished reading buffer a^1
+                const int next = tile + gridDim.x;
+                if (has_res && next < total_tiles) issue_res(next, a ^ 1);
+            }
+            mbar_wait(bar_tfull + a * 8, aph);
+            tc_fence_after();
+            if (has_res) mbar_wait(bar_rfull + a * 8, aph);
+            const uint32_t row_addr = e_base + a * L::EPI_BYTES + static_cast<uint32_t>(t) * 128u;
+            const uint32_t tmem_acc = tmem_base + a * BLOCK_N + (static_cast<uint32_t>(q4 * 32) << 16);
+#pragma unroll 1
+            for (int c = grp * (BLOCK_N / 64); c < (grp + 1) * (BLOCK_N / 64); ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_acc + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = c * 32 + q * 8;
+                    const uint32_t addr = row_addr + (col >> 6) * (TILE_M * 128) + ((((col & 63) >> 3) ^ sw) << 4);
+                    float f[8];
+                    const float4 b0 = *reinterpret_cast<const float4*>(sbias + n0 + col);
+                    const float4 b1 = *reinterpret_cast<const float4*>(sbias + n0 + col + 4);
+                    f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
+                    if (has_res) {
+                        uint32_t ru[4];
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ru[0]), "=r"(ru[1]), "=r"(ru[2]), "=r"(ru[3]) : "r"(addr));
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 rf = DT<T>::unpack2(ru[e]);
+                            f[2 * e] += rf.x;
+                            f[2 * e + 1] += rf.y;
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                    }
+                    const uint32_t o0 = DT<T>::pack2(f[0], f[1]), o1 = DT<T>::pack2(f[2], f[3]);
+                    const uint32_t o2 = DT<T>::pack2(f[4], f[5]), o3 = DT<T>::pack2(f[6], f[7]);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + a * 8);        // accumulator a may be overwritten
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (leader) {
+#pragma unroll
+                for (int bx = 0; bx < BOXES; ++bx)
+                    tma_store_2d(&maps.out, e_base + a * L::EPI_BYTES + bx * (TILE_M * 128), p.out_coff + n0 + bx * 64, m_tile * TILE_M);
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_read0();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -443,6 +670,32 @@ bool conv_tc_make_weight_tmap(ConvWeights& w) {
 }
 
 static int g_force_gather = -1;     // SPECB200_FORCE_GATHER=1 disables the TMA im2col path (debug / A-B test)
+static int g_no_persist = -1;       // SPECB200_NO_PERSIST=1 keeps the one-tile-per-CTA kernel (A-B test)
+static int g_num_sms = 0;
+
+template <typename T, int BLOCK_N, int STAGES>
+static bool launch_persistent(const ConvParams& p, const ConvTcMaps& maps, int mode, int m_tiles, int n_tiles, cudaStream_t s) {
+    using L = ConvTcpSmem<BLOCK_N, STAGES>;
+    auto k0 = conv_tcp_kernel<T, BLOCK_N, STAGES, A_TILED>;
+    auto k1 = conv_tcp_kernel<T, BLOCK_N, STAGES, A_IM2COL>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (!check_cuda(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        if (!check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        attr_done = true;
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!check_cuda(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev), "sm count")) return false;
+    }
+    const long long total = static_cast<long long>(m_tiles) * n_tiles;
+    if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles"); return false; }
+    const unsigned grid = static_cast<unsigned>(total < g_num_sms ? total : g_num_sms);
+    if (mode == A_TILED) k0<<<grid, CONV_TCP_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles, static_cast<int>(total));
+    else k1<<<grid, CONV_TCP_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles, static_cast<int>(total));
+    return check_cuda(cudaGetLastError(), "conv_tcp launch");
+}
 
 template <typename T, int BLOCK_N, int STAGES>
 static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s) {
@@ -466,6 +719,12 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
         if (!make_tmap_2d(&maps.out, p.out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.out_ld), static_cast<uint64_t>(p.out_ld), TILE_M)) return false;
         if (p.res != nullptr &&
             !make_tmap_2d(&maps.res, p.res, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.res_ld), static_cast<uint64_t>(p.res_ld), TILE_M)) return false;
+    }
+    if (g_no_persist < 0) { const char* e = getenv("SPECB200_NO_PERSIST"); g_no_persist = (e && e[0] == '1') ? 1 : 0; }
+    if constexpr (BLOCK_N == 64 || BLOCK_N == 128) {
+        const bool mma_bound = p.kh * p.kw > 1;                  // measured: two co-resident one-tile CTAs feed the tensor pipe better
+        if (!g_no_persist && !mma_bound && (mode == A_TILED || mode == A_IM2COL) && (p.Cout & 63) == 0 && p.Cout <= 2048)
+            return launch_persistent<T, BLOCK_N, (BLOCK_N == 128 ? 4 : 6)>(p, maps, mode, m_tiles, n_tiles, s);
     }
     auto k0 = conv_tc_kernel<T, BLOCK_N, STAGES, A_TILED>;
     auto k1 = conv_tc_kernel<T, BLOCK_N, STAGES, A_IM2COL>;

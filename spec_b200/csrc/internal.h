@@ -30,6 +30,7 @@ struct ConvWeights {
     int cout = 0, cin = 0, kh = 0, kw = 0;
     int K = 0, K_pad = 0, cout_pad = 0, block_n = 0;
     int kwp = 0;               // > 0: stem layout (Cin stored = 4, kw padded to kwp)
+    bool stem7 = false;        // packed for conv_stem7_kernel: k = (c*7 + kh)*8 + kw, K = 168 -> 192
     void* w_tc = nullptr;      // [cout_pad][K_pad] 16-bit, K-major (tcgen05 path)
     float* w_f32 = nullptr;    // [K][cout] fp32 (SIMT parity path)
     float* bias = nullptr;     // [cout]
@@ -44,6 +45,10 @@ bool check_cuda(cudaError_t e, const char* what);
 bool conv_tc_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s);
 bool conv_tc_make_weight_tmap(ConvWeights& w);
 int conv_tc_pick_block_n(int cout);
+
+// dedicated 7x7/2 stem (conv_stem.cu): reads the fp32 NCHW image directly, writes NHWC 16-bit [N,Ho,Wo,64]
+bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N, int H, int W, int Ho, int Wo, int prec,
+                       cudaStream_t s);
 
 // fp32 SIMT implicit-GEMM conv and linear (conv_simt.cu).
 bool conv_f32_launch(const ConvParams& p, const ConvWeights& w, cudaStream_t s);

@@ -96,14 +96,14 @@ def test_conv_kernels(case, precision):
 
 
 def test_stem_conv7x7_and_maxpool():
-    for precision in ('bf16', 'fp32'):
+    for precision, (H, W) in (('bf16', (64, 96)), ('bf16', (70, 100)), ('fp16', (37, 53)), ('fp32', (64, 96))):
         def builder(root, P):
             x = P.conv(root, 0, 3, 64, 7, 2, 3, 'conv1', 'bn1', True)
             y = P.op(2, x, P.new(64))
             return y, 64
         t = Trunk('custom', builder=builder, precision=precision)
         randomize_module_(t, 5)
-        x = torch.randn(2, 3, 64, 96)
+        x = torch.randn(3, 3, H, W)          # odd sizes: partial 8x16 tiles of the dedicated stem kernel
         dt = TORCH_DT[precision]
         ref = torch.nn.functional.max_pool2d(lowp.conv_bn_act(lowp._rnd(x, dt), t.conv1, t.bn1, dt, True), 3, 2, 1)
         got = t.to(DEV)(x.to(DEV))
