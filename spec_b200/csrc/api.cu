@@ -467,7 +467,7 @@ extern "C" void specb200_camtail_destroy(specb200_camtail_t* t) {
 struct specb200_hmrtail {
     int C = 0, use_cam_feats = 0, use_cam = 0, ldx = 0, kin = 0;
     float focal = 5000.f, img_res = 224.f;
-    float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr, *dec_w = nullptr, *dec_b = nullptr, *init157 = nullptr;
+    float *Fx = nullptr, *c0 = nullptr, *AsT = nullptr, *init157 = nullptr;   // folded head (see tail.cu)
     float *Vt = nullptr, *Sd = nullptr, *Pd = nullptr, *Wl = nullptr, *Jx = nullptr, *Jt = nullptr, *Js = nullptr;
     int64_t last_launches = 0;
 };
@@ -496,20 +496,43 @@ extern "C" int specb200_hmrtail_create(specb200_hmrtail_t** out, const specb200_
     t->ldx = static_cast<int>(align_up(t->kin, 4));
     const int NV = SMPL_NV, VP = SMPL_VP;
     bool ok = true;
-    {   // fc1: [1024][kin] -> row stride ldx (zero padded) so that every K slice is 16-byte aligned
-        std::vector<float> w(static_cast<size_t>(1024) * t->ldx, 0.f);
-        for (int o = 0; o < 1024; ++o) memcpy(&w[static_cast<size_t>(o) * t->ldx], p->fc1_w + static_cast<size_t>(o) * t->kin, sizeof(float) * t->kin);
-        ok = ok && upload(&t->fc1_w, w);
-        ok = ok && upload(&t->fc1_b, std::vector<float>(p->fc1_b, p->fc1_b + 1024));
-        ok = ok && upload(&t->fc2_w, std::vector<float>(p->fc2_w, p->fc2_w + 1024 * 1024));
-        ok = ok && upload(&t->fc2_b, std::vector<float>(p->fc2_b, p->fc2_b + 1024));
-        std::vector<float> dw(static_cast<size_t>(157) * 1024), db(157), init(157);
-        memcpy(&dw[0], p->decpose_w, sizeof(float) * 144 * 1024);
-        memcpy(&dw[144 * 1024], p->decshape_w, sizeof(float) * 10 * 1024);
-        memcpy(&dw[154 * 1024], p->deccam_w, sizeof(float) * 3 * 1024);
-        memcpy(&db[0], p->decpose_b, sizeof(float) * 144); memcpy(&db[144], p->decshape_b, sizeof(float) * 10); memcpy(&db[154], p->deccam_b, sizeof(float) * 3);
+    {   // fold the affine head in fp64:  P = D W2 ; Q = P W1 ; c0 = P b1 + D b2 + bd
+        const int kin = t->kin, C = t->C, ns = kin - C;
+        std::vector<double> D(static_cast<size_t>(157) * 1024), bd(157);
+        for (int i = 0; i < 144 * 1024; ++i) D[i] = p->decpose_w[i];
+        for (int i = 0; i < 10 * 1024; ++i) D[144 * 1024 + i] = p->decshape_w[i];
+        for (int i = 0; i < 3 * 1024; ++i) D[154 * 1024 + i] = p->deccam_w[i];
+        for (int i = 0; i < 144; ++i) bd[i] = p->decpose_b[i];
+        for (int i = 0; i < 10; ++i) bd[144 + i] = p->decshape_b[i];
+        for (int i = 0; i < 3; ++i) bd[154 + i] = p->deccam_b[i];
+        std::vector<double> P(static_cast<size_t>(157) * 1024, 0.0);
+        for (int i = 0; i < 157; ++i)
+            for (int k = 0; k < 1024; ++k) {
+                const double d = D[static_cast<size_t>(i) * 1024 + k];
+                const float* w2 = p->fc2_w + static_cast<size_t>(k) * 1024;
+                double* pr = &P[static_cast<size_t>(i) * 1024];
+                for (int j = 0; j < 1024; ++j) pr[j] += d * w2[j];
+            }
+        std::vector<double> Q(static_cast<size_t>(157) * kin, 0.0);
+        std::vector<float> c0(160, 0.f);
+        for (int i = 0; i < 157; ++i) {
+            double c = bd[i];
+            for (int k = 0; k < 1024; ++k) {
+                const double pv = P[static_cast<size_t>(i) * 1024 + k];
+                c += pv * p->fc1_b[k] + D[static_cast<size_t>(i) * 1024 + k] * p->fc2_b[k];
+                const float* w1 = p->fc1_w + static_cast<size_t>(k) * kin;
+                double* qr = &Q[static_cast<size_t>(i) * kin];
+                for (int j = 0; j < kin; ++j) qr[j] += pv * w1[j];
+            }
+            c0[i] = static_cast<float>(c);
+        }
+        std::vector<float> Fx(static_cast<size_t>(157) * C), AsT(static_cast<size_t>(164) * 160, 0.f), init(157);
+        for (int i = 0; i < 157; ++i) {
+            for (int j = 0; j < C; ++j) Fx[static_cast<size_t>(i) * C + j] = static_cast<float>(Q[static_cast<size_t>(i) * kin + j]);
+            for (int k = 0; k < ns; ++k) AsT[static_cast<size_t>(k) * 160 + i] = static_cast<float>(Q[static_cast<size_t>(i) * kin + C + k]);
+        }
         memcpy(&init[0], p->init_pose, sizeof(float) * 144); memcpy(&init[144], p->init_shape, sizeof(float) * 10); memcpy(&init[154], p->init_cam, sizeof(float) * 3);
-        ok = ok && upload(&t->dec_w, dw) && upload(&t->dec_b, db) && upload(&t->init157, init);
+        ok = ok && upload(&t->Fx, Fx) && upload(&t->c0, c0) && upload(&t->AsT, AsT) && upload(&t->init157, init);
     }
     {   // SMPL constants, repacked coordinate-planar over a padded vertex axis (coalesced over vertices)
         std::vector<float> Vt(3 * static_cast<size_t>(VP), 0.f), Sd(30 * static_cast<size_t>(VP), 0.f), Pd(207 * 3 * static_cast<size_t>(VP), 0.f),
@@ -550,15 +573,14 @@ extern "C" int specb200_hmrtail_create(specb200_hmrtail_t** out, const specb200_
 }
 
 namespace {
-struct HmrWs { float *X, *Fx, *H1, *H2, *pf, *A, *Jp, *part; size_t total; };
+constexpr int HEAD_KSPLIT = 8;     // split-K slices of the G GEMM (N = 157 alone would fill only 24 CTAs)
+struct HmrWs { float *X, *G, *pf, *A, *Jp, *part; size_t total; };
 HmrWs hmr_carve(const specb200_hmrtail* t, int B, void* base) {
     HmrWs w;
     size_t off = 0;
     auto take = [&](size_t nfloat) { float* p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + off); off += align_up(nfloat * sizeof(float), 256); return p; };
     w.X = take(static_cast<size_t>(B) * t->ldx);
-    w.Fx = take(static_cast<size_t>(B) * 1024);
-    w.H1 = take(static_cast<size_t>(B) * 1024);
-    w.H2 = take(static_cast<size_t>(B) * 1024);
+    w.G = take(static_cast<size_t>(B) * 160 * HEAD_KSPLIT);
     w.pf = take(static_cast<size_t>(B) * PF_LD);
     w.A = take(static_cast<size_t>(B) * 288);
     w.Jp = take(static_cast<size_t>(B) * 72);
@@ -590,15 +612,9 @@ extern "C" int specb200_hmrtail_forward(specb200_hmrtail_t* t, int32_t B, void* 
     const HmrWs w = hmr_carve(t, B, workspace);
     const int C = t->C, ldx = t->ldx;
     int64_t n = 0;
-    if (!head_init_launch(w.X, ldx, C, t->init157, cam_rotmat, cam_intr, img_h, t->use_cam_feats, B, s)) return 1; ++n;
-    // fc1 split: the feature part is iteration-invariant.  Fx = xf W1[:, :C]^T + b1
-    if (!linear_f32_launch(w.X, ldx, t->fc1_w, ldx, t->fc1_b, nullptr, 0, w.Fx, 1024, B, 1024, C, s)) return 1; ++n;
-    const int kstate = ldx - C;   // state (157) + cam feats (7) + zero padding
-    for (int it = 0; it < 3; ++it) {
-        if (!linear_f32_launch(w.X + C, ldx, t->fc1_w + C, ldx, nullptr, w.Fx, 1024, w.H1, 1024, B, 1024, kstate, s)) return 1; ++n;
-        if (!linear_f32_launch(w.H1, 1024, t->fc2_w, 1024, t->fc2_b, nullptr, 0, w.H2, 1024, B, 1024, 1024, s)) return 1; ++n;
-        if (!linear_f32_launch(w.H2, 1024, t->dec_w, 1024, t->dec_b, w.X + C, ldx, w.X + C, ldx, B, 157, 1024, s)) return 1; ++n;
-    }
+    // G = xf (D W2 W1[:, :C])^T + c0 : the only GEMM of the folded head
+    if (!linear_f32_launch(w.X, ldx, t->Fx, C, t->c0, nullptr, 0, w.G, 160, B, 157, C, s, HEAD_KSPLIT, static_cast<size_t>(B) * 160)) return 1; ++n;
+    if (!head_iter_launch(w.X, ldx, C, w.G, HEAD_KSPLIT, t->AsT, t->init157, cam_rotmat, cam_intr, img_h, t->use_cam_feats, B, s)) return 1; ++n;
     if (!smpl_prep_launch(w.X, ldx, C, t->Jt, t->Js, w.pf, w.A, w.Jp, o->pred_pose, o->ld_pose, o->pred_pose_6d, o->ld_pose_6d,
                           o->pred_shape, o->ld_shape, o->pred_cam, o->ld_cam, B, s)) return 1; ++n;
     if (!smpl_verts_launch(t->Vt, t->Sd, t->Pd, t->Wl, t->Jx, w.X, ldx, C, w.pf, w.A, o->smpl_vertices, o->ld_vertices, w.part, B, s)) return 1; ++n;
@@ -613,7 +629,7 @@ extern "C" int64_t specb200_hmrtail_last_launches(specb200_hmrtail_t* t) { retur
 
 extern "C" void specb200_hmrtail_destroy(specb200_hmrtail_t* t) {
     if (!t) return;
-    float* ptrs[] = {t->fc1_w, t->fc1_b, t->fc2_w, t->fc2_b, t->dec_w, t->dec_b, t->init157, t->Vt, t->Sd, t->Pd, t->Wl, t->Jx, t->Jt, t->Js};
+    float* ptrs[] = {t->Fx, t->c0, t->AsT, t->init157, t->Vt, t->Sd, t->Pd, t->Wl, t->Jx, t->Jt, t->Js};
     for (float* p : ptrs) if (p) cudaFree(p);
     delete t;
 }

@@ -122,8 +122,15 @@ constexpr int LN_BM = 32, LN_BN = 64, LN_BK = 32;
 __global__ void __launch_bounds__(256)
 linear_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                   const float* __restrict__ bias, const float* add, int add_ld, float* out, int out_ld,
-                  int M, int N, int K)
+                  int M, int N, int K, int k_chunk, size_t split_stride)
 {
+    // split-K: slice blockIdx.z handles k in [z*k_chunk, min(K, (z+1)*k_chunk)) and writes its partial sums to
+    // out + z*split_stride (bias / addend only in slice 0); the consumer adds the slices in a fixed order.
+    const int kz0 = blockIdx.z * k_chunk;
+    A += kz0; W += kz0;
+    K = min(K - kz0, k_chunk);
+    out += blockIdx.z * split_stride;
+    if (blockIdx.z != 0) { bias = nullptr; add = nullptr; }
     __shared__ __align__(16) float As[LN_BK][LN_BM + 4];
     __shared__ __align__(16) float Ws[LN_BK][LN_BN + 4];
     const int tid = threadIdx.x;
@@ -176,14 +183,19 @@ linear_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict_
 }
 
 bool linear_f32_launch(const float* A, int lda, const float* W, int ldw, const float* bias, const float* add,
-                       int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s) {
+                       int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s, int ksplit,
+                       size_t split_stride) {
     if ((K % 4) != 0 || (lda % 4) != 0 || (ldw % 4) != 0 ||
         (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(W) & 15) != 0) {
         set_error("linear_f32: K, lda, ldw must be multiples of 4 and pointers 16-byte aligned");
         return false;
     }
-    dim3 grid((N + LN_BN - 1) / LN_BN, (M + LN_BM - 1) / LN_BM);
-    linear_f32_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldw, bias, add, add_ld, out, out_ld, M, N, K);
+    if (ksplit < 1) ksplit = 1;
+    int k_chunk = (K + ksplit - 1) / ksplit;
+    k_chunk = (k_chunk + 3) / 4 * 4;
+    ksplit = (K + k_chunk - 1) / k_chunk;
+    dim3 grid((N + LN_BN - 1) / LN_BN, (M + LN_BM - 1) / LN_BM, ksplit);
+    linear_f32_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldw, bias, add, add_ld, out, out_ld, M, N, K, k_chunk, split_stride);
     return check_cuda(cudaGetLastError(), "linear_f32 launch");
 }
 

@@ -20,16 +20,16 @@ namespace sb {
 constexpr int ST_TH = 8, ST_TW = 16;                 // output tile
 constexpr int ST_PR = 2 * ST_TH + 5;                 // 21 patch rows
 constexpr int ST_PC = 2 * ST_TW + 5;                 // 37 patch cols
-constexpr int ST_PP = 40;                            // patch row pitch (elements)
+constexpr int ST_PP = 48;                            // patch row pitch (elements): 2 rows = 48 words -> the two
+                                                     // half-warps of the A build hit disjoint banks
 constexpr int ST_KB = 3;                             // K = 192 = 3 x 64
 constexpr int ST_A_BYTES = ST_KB * 128 * 128;        // 49152
 constexpr int ST_B_BYTES = ST_KB * 64 * 128;         // 24576
 constexpr int ST_STAGE_BYTES = 128 * 128;            // 16384
-constexpr int ST_PATCH_BYTES = 3 * ST_PR * ST_PP * 2;    // 5040
 constexpr int ST_OFF_B = ST_A_BYTES;
 constexpr int ST_OFF_STAGE = ST_OFF_B + ST_B_BYTES;
 constexpr int ST_OFF_PATCH = ST_OFF_STAGE + ST_STAGE_BYTES;
-constexpr int ST_OFF_BIAS = ST_OFF_PATCH + 5120;
+constexpr int ST_OFF_BIAS = ST_OFF_PATCH + 6144;      // patch = 3*21*48*2 = 6048 B
 constexpr int ST_OFF_BAR = ST_OFF_BIAS + 256;
 constexpr int ST_DYN_BYTES = ST_OFF_BAR + 64 + 1024;
 
@@ -76,26 +76,45 @@ conv_stem7_kernel(const float* __restrict__ img, T* __restrict__ out, const floa
     mbar_wait(bar_b, 0);
 
     const size_t plane = static_cast<size_t>(H) * W;
+    // patch loader role: warp w owns patch rows w, w+8, ... (63 rows = 3 channels x 21); lanes cover cols lane, lane+32
+    float pre[16];
+    auto prefetch = [&](int tile) {
+        const int tw = tile % tiles_w;
+        const int th = (tile / tiles_w) % tiles_h;
+        const int n = tile / (tiles_w * tiles_h);
+        const int ih0 = 2 * th * ST_TH - 3, iw0 = 2 * tw * ST_TW - 3;
+        const float* src = img + static_cast<size_t>(n) * 3 * plane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int row = warp + 8 * k;                        // < 63 checked below
+            const int c = row >= 42 ? 2 : (row >= 21 ? 1 : 0);
+            const int r = row - c * 21;
+            const int ih = ih0 + r;
+            const bool rok = row < 63 && static_cast<unsigned>(ih) < static_cast<unsigned>(H);
+            const float* rp = src + c * plane + static_cast<size_t>(rok ? ih : 0) * W;
+            const int iwa = iw0 + lane, iwb = iw0 + lane + 32;
+            pre[2 * k] = (rok && static_cast<unsigned>(iwa) < static_cast<unsigned>(W)) ? __ldg(rp + iwa) : 0.f;
+            pre[2 * k + 1] = (rok && lane < ST_PC - 32 && static_cast<unsigned>(iwb) < static_cast<unsigned>(W)) ? __ldg(rp + iwb) : 0.f;
+        }
+    };
+    if (static_cast<int>(blockIdx.x) < total_tiles) prefetch(blockIdx.x);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int tw = tile % tiles_w;
         const int th = (tile / tiles_w) % tiles_h;
         const int n = tile / (tiles_w * tiles_h);
         const int oh0 = th * ST_TH, ow0 = tw * ST_TW;
-        const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
-        // ---- 1. input patch -> smem (16 bit)
-        const float* src = img + static_cast<size_t>(n) * 3 * plane;
-        for (int i = tid; i < 3 * ST_PR * ST_PC; i += 256) {
-            const int c = i / (ST_PR * ST_PC);
-            const int rem = i - c * (ST_PR * ST_PC);
-            const int r = rem / ST_PC, col = rem - r * ST_PC;
-            const int ih = ih0 + r, iw = iw0 + col;
-            float v = 0.f;
-            if (static_cast<unsigned>(ih) < static_cast<unsigned>(H) && static_cast<unsigned>(iw) < static_cast<unsigned>(W))
-                v = __ldg(src + c * plane + static_cast<size_t>(ih) * W + iw);
-            patch[(c * ST_PR + r) * ST_PP + col] = DT<T>::from_f(v);
+        // ---- 1. input patch (prefetched into registers during the previous tile) -> smem, 16 bit
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int row = warp + 8 * k;
+            if (row < 63) {
+                patch[row * ST_PP + lane] = DT<T>::from_f(pre[2 * k]);
+                if (lane < ST_PC - 32) patch[row * ST_PP + lane + 32] = DT<T>::from_f(pre[2 * k + 1]);
+            }
         }
         __syncthreads();
+        if (tile + static_cast<int>(gridDim.x) < total_tiles) prefetch(tile + gridDim.x);   // overlaps phases 2-5
         // ---- 2. A rows from the patch: thread pair (t, half) builds 12 of the 24 chunks of row t
         {
             const int t = tid & 127, half = tid >> 7;

@@ -53,8 +53,10 @@ bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N,
 // fp32 SIMT implicit-GEMM conv and linear (conv_simt.cu).
 bool conv_f32_launch(const ConvParams& p, const ConvWeights& w, cudaStream_t s);
 // out[M, n0:n0+N] (ld out_ld) = A[M,K](ld lda) @ W[N,K]^T (ld ldw) + bias[N] + add[M,N](ld add_ld) ; fp32
+// ksplit > 1: split-K partial sums, slice z written to out + z*split_stride (consumer adds them in order)
 bool linear_f32_launch(const float* A, int lda, const float* W, int ldw, const float* bias, const float* add,
-                       int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s);
+                       int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s, int ksplit = 1,
+                       size_t split_stride = 0);
 
 // elementwise / layout kernels (elementwise.cu)
 bool images_to_nhwc_launch(const float* img_nchw, void* out_nhwc, int N, int H, int W, int cpad, int prec, cudaStream_t s);

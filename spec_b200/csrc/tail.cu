@@ -100,30 +100,51 @@ bool camcalib_decode_launch(const float* logits, int ld, int D, const float* img
     return check_cuda(cudaGetLastError(), "camcalib_decode");
 }
 
-// ------------------------------------------------------------------ head state init
+// ------------------------------------------------------------------ HMR head (folded iterative regressor)
 // X row layout: [xf (C) | pose6d (144) | shape (10) | cam (3) | R6d (6) | vfov (1)]   (last 7 only with cam feats)
-__global__ void head_init_kernel(float* __restrict__ X, int ldx, int C, const float* __restrict__ init157,
-                                 const float* __restrict__ cam_rotmat, const float* __restrict__ cam_intr,
-                                 const float* __restrict__ img_h, int use_cam_feats, int B)
+// The reference iterates  xc = fc2(fc1(cat[xf, s, camfeat]));  s += dec(xc)  three times with dropout = identity and
+// NO non-linearity in between (pare HMRHead), so one iteration is affine in (xf, s, camfeat):
+//     s <- s + G + As [s; camfeat],   G = (D W2 W1[:, :C]) xf + (D (W2 b1 + b2) + bd),   As = D W2 W1[:, C:]
+// The products are folded once at create time in fp64 (api.cu); per forward this leaves ONE (B x C) x (C x 157)
+// GEMM for G and three 157 x 164 mat-vecs per image, done here (one CTA per image, AsT is [k][160] so lanes read
+// unit-stride).  Same trick as BatchNorm folding: exact in real arithmetic, rounding differs at the 1e-7 level.
+__global__ void __launch_bounds__(192)
+head_iter_kernel(float* __restrict__ X, int ldx, int C, const float* __restrict__ G /*[gsplit][B][160]*/, int gsplit,
+                 const float* __restrict__ AsT /*[ns][160]*/, const float* __restrict__ init157,
+                 const float* __restrict__ cam_rotmat, const float* __restrict__ cam_intr,
+                 const float* __restrict__ img_h, int use_cam_feats, int n_iter, int B)
 {
-    const int b = blockIdx.x;
-    float* row = X + static_cast<size_t>(b) * ldx + C;
-    for (int i = threadIdx.x; i < 157; i += blockDim.x) row[i] = init157[i];
-    // zero the alignment padding behind the valid columns (the matching fc1 weight columns are zero,
-    // but 0 * garbage could still be NaN)
-    for (int i = 157 + (use_cam_feats ? 7 : 0) + threadIdx.x; i < ldx - C; i += blockDim.x) row[i] = 0.f;
-    if (use_cam_feats && threadIdx.x < 7) {
-        const int i = threadIdx.x;
-        float v;
-        if (i < 6) v = cam_rotmat[b * 9 + (i >> 1) * 3 + (i & 1)];                          // R[:, :2] row-major
-        else v = 2.f * atanf(img_h[b] / (2.f * cam_intr[b * 9]));                            // hmr.py:95
-        row[157 + i] = v;
+    __shared__ float v[164];
+    const int b = blockIdx.x, j = threadIdx.x;
+    const int ns = 157 + (use_cam_feats ? 7 : 0);
+    if (j < 157) v[j] = init157[j];
+    else if (j < ns) {
+        const int i = j - 157;
+        v[j] = (i < 6) ? cam_rotmat[b * 9 + (i >> 1) * 3 + (i & 1)]                           // R[:, :2] row-major
+                       : 2.f * atanf(img_h[b] / (2.f * cam_intr[b * 9]));                      // hmr.py:95
     }
+    float g = 0.f;                                             // sum the split-K slices in a fixed order
+    if (j < 157)
+        for (int z = 0; z < gsplit; ++z) g += G[(static_cast<size_t>(z) * B + b) * 160 + j];
+    for (int it = 0; it < n_iter; ++it) {
+        __syncthreads();
+        float acc = g;
+        if (j < 157) {
+#pragma unroll 4
+            for (int k = 0; k < ns; ++k) acc = fmaf(AsT[k * 160 + j], v[k], acc);
+        }
+        __syncthreads();
+        if (j < 157) v[j] += acc;
+    }
+    __syncthreads();
+    float* row = X + static_cast<size_t>(b) * ldx + C;
+    if (j < 157) row[j] = v[j];
 }
-bool head_init_launch(float* X, int ldx, int C, const float* init157, const float* cam_rotmat, const float* cam_intr,
-                      const float* img_h, int use_cam_feats, int B, cudaStream_t s) {
-    head_init_kernel<<<B, 64, 0, s>>>(X, ldx, C, init157, cam_rotmat, cam_intr, img_h, use_cam_feats, B);
-    return check_cuda(cudaGetLastError(), "head_init");
+bool head_iter_launch(float* X, int ldx, int C, const float* G, int gsplit, const float* AsT, const float* init157,
+                      const float* cam_rotmat, const float* cam_intr, const float* img_h, int use_cam_feats, int B,
+                      cudaStream_t s) {
+    head_iter_kernel<<<B, 192, 0, s>>>(X, ldx, C, G, gsplit, AsT, init157, cam_rotmat, cam_intr, img_h, use_cam_feats, 3, B);
+    return check_cuda(cudaGetLastError(), "head_iter");
 }
 
 // ------------------------------------------------------------------ SMPL prep: rot6d, rest joints, kinematic chain

@@ -13,8 +13,9 @@ bool tail_upload_tables(const int* joint_map49, const int* vertex_ids21);
 
 bool camcalib_decode_launch(const float* logits, int ld, int D, const float* img_h, const float* img_w, float* angles,
                             float* rotmat, float* intr, float* fpix, int B, cudaStream_t s);
-bool head_init_launch(float* X, int ldx, int C, const float* init157, const float* cam_rotmat, const float* cam_intr,
-                      const float* img_h, int use_cam_feats, int B, cudaStream_t s);
+bool head_iter_launch(float* X, int ldx, int C, const float* G, int gsplit, const float* AsT, const float* init157,
+                      const float* cam_rotmat, const float* cam_intr, const float* img_h, int use_cam_feats, int B,
+                      cudaStream_t s);
 bool smpl_prep_launch(const float* X, int ldx, int C, const float* Jt, const float* Js, float* pf, float* Amat,
                       float* Jposed, float* o_pose, long long ld_pose, float* o_pose6d, long long ld_pose6d,
                       float* o_shape, long long ld_shape, float* o_cam, long long ld_cam, int B, cudaStream_t s);
