@@ -27,6 +27,11 @@
 //   warp 4     TMA producer (A and B); owns the TMEM allocation.
 //   warp 5     MMA issuer: one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage and
 //              commits stage release / accumulator-ready to mbarriers.
+//   warps 6-9  second epilogue group: in the TMA-store epilogue they convert the upper half of the columns.
+//
+// BLOCK_N = 256 (3x3 convs with Cout >= 256): at 128 x 128 tiles the tensor pipe consumes 128 B/cycle of operands,
+// so covering ~1.5k cycles of TMA latency needs ~190 KB in flight -- more than one SM's smem; a 128 x 256 tile needs
+// 96 B/cycle.  One CTA per SM then (4 stages x 48 KB), so the epilogue gets both groups to stay short.
 //
 // Pipeline: STAGES-deep smem ring with full/empty mbarriers; smem footprint <= ~100 KB so two CTAs
 // share an SM and one CTA's epilogue overlaps the other's main loop.
@@ -39,7 +44,7 @@ constexpr int TILE_M = 128;
 constexpr int TILE_K = 64;                      // 64 x 16-bit = 128 B = one swizzle row
 constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;
 constexpr int GATHER_LAG = 2;                   // cp.async groups kept in flight per producer thread
-constexpr int CONV_TC_THREADS = 192;
+constexpr int CONV_TC_THREADS = 320;           // warps 0-3 epilogue A (+gather), 4 TMA, 5 MMA, 6-9 epilogue B
 enum { A_TILED = 0, A_IM2COL = 1, A_GATHER = 2, A_STEM = 3 };
 
 template <int BLOCK_N, int STAGES>
@@ -120,11 +125,14 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_ptr_s;
 
-    if (warp < 4) {
-        const int t = threadIdx.x;                               // tile row == TMEM lane
+    if (warp < 4 || warp >= 6) {
+        const int grp = warp >= 6 ? 1 : 0;                       // epilogue group (column half in the TMA epilogue)
+        const int q4 = warp & 3;                                 // TMEM lane quarter this warp may access
+        const int t = q4 * 32 + lane;                            // tile row == TMEM lane
         const long long r = static_cast<long long>(m_tile) * TILE_M + t;
         const bool row_ok = r < p.M;
         // ---------------- A producer (software im2col)
+        if (grp == 0)
         if constexpr (A_MODE == A_GATHER || A_MODE == A_STEM) {
             const T* __restrict__ in = static_cast<const T*>(p.in);
             int n = 0, oh = 0, ow = 0;
@@ -208,7 +216,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
             const uint32_t stage_tile = a_base;                   // [BLOCK_N/64][128 rows][128 B], 128B-swizzled
             const bool has_res = p.res != nullptr;
             if (has_res) {
-                if (t == 0) {
+                if (grp == 0 && t == 0) {
                     mbar_arrive_expect_tx(bar_res, L::EPI_BYTES);
 #pragma unroll
                     for (int bx = 0; bx < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++bx)
@@ -219,9 +227,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
             const uint32_t row_addr = stage_tile + static_cast<uint32_t>(t) * 128u;
             const uint32_t sw = static_cast<uint32_t>(t) & 7u;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = grp * (BLOCK_N / 64); c < (grp + 1) * (BLOCK_N / 64); ++c) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+                tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q4 * 32) << 16) + c * 32, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -250,8 +258,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
                 }
             }
             fence_proxy_async_smem();                             // generic-proxy smem writes -> TMA store reads
-            named_bar_sync(1, 128);
-            if (t == 0) {
+            named_bar_sync(1, 256);
+            if (grp == 0 && t == 0) {
 #pragma unroll
                 for (int bx = 0; bx < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++bx)
                     if (n0 + bx * 64 < p.Cout)
@@ -259,7 +267,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
                 tma_store_commit();
                 tma_store_wait_read0();                           // smem must stay valid until the store has read it
             }
-        } else {
+        } else if (grp == 0) {
             T* __restrict__ out = static_cast<T*>(p.out);
             const T* __restrict__ res = static_cast<const T*>(p.res);
             const size_t out_row = static_cast<size_t>(r) * p.out_ld + p.out_coff;
@@ -267,7 +275,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+                tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q4 * 32) << 16) + c * 32, v);
                 tmem_ld_wait();
                 if (row_ok) {
 #pragma unroll
@@ -655,9 +663,13 @@ static bool make_tmap_im2col(CUtensorMap* m, const ConvParams& p) {
     return true;
 }
 
-int conv_tc_pick_block_n(int cout) {
+int conv_tc_pick_block_n(int cout, int taps) {
     if (cout <= 32) return 32;
     if (cout <= 64) return 64;
+    if (taps > 1 && cout >= 256 && (cout % 256) == 0) {
+        const char* e = getenv("SPECB200_NO_N256");
+        if (!(e && e[0] == '1')) return 256;
+    }
     return 128;
 }
 
@@ -754,6 +766,7 @@ static bool launch_dt(const ConvParams& p, const ConvWeights& w, cudaStream_t s)
         case 32: return launch_cfg<T, 32, 4>(p, w, s);
         case 64: return launch_cfg<T, 64, 4>(p, w, s);
         case 128: return launch_cfg<T, 128, 3>(p, w, s);
+        case 256: return launch_cfg<T, 256, 4>(p, w, s);
         default: set_error("conv_tc: unsupported block_n"); return false;
     }
 }
