@@ -50,6 +50,7 @@ typedef struct specb200_op {
     int32_t dst_coff; /* channel offset inside dst (concat)                                  */
     int32_t shift;    /* UPADD: log2 of the upsampling factor                                */
     int32_t wslot;    /* conv: weight slot                                                   */
+    int32_t pair;     /* conv 3x3/1 with cin=cout=32: run on the pixel-pair view [H][W/2][64] */
 } specb200_op_t;
 
 typedef struct specb200_trunk specb200_trunk_t;

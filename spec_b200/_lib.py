@@ -15,7 +15,7 @@ PREC = {'fp32': 0, 'bf16': 1, 'fp16': 2}
 
 class Op(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('type', 'src', 'src2', 'dst', 'cin', 'cout', 'kh', 'kw', 'stride', 'pad',
-                                          'relu', 'dst_coff', 'shift', 'wslot')]
+                                          'relu', 'dst_coff', 'shift', 'wslot', 'pair')]
 
 
 _F = C.POINTER(C.c_float)

@@ -69,13 +69,16 @@ class _Program:
             dst = self.new(cout)
         wslot = len(self.convs)
         self.convs.append((conv_path, bn_path, cout, cin, k))
+        # 32 -> 32 channel 3x3/1 convs (HRNet's high-resolution branch) run on the pixel-pair view of the same memory
+        pair = int(cin == 32 and cout == 32 and k == 3 and stride == 1 and pad == 1 and coff == 0 and src != 0)
         self.ops.append(dict(type=OP_CONV, src=src, src2=-1 if res is None else res, dst=dst, cin=cin, cout=cout,
-                             kh=k, kw=k, stride=stride, pad=pad, relu=int(relu), dst_coff=coff, shift=0, wslot=wslot))
+                             kh=k, kw=k, stride=stride, pad=pad, relu=int(relu), dst_coff=coff, shift=0, wslot=wslot,
+                             pair=pair))
         return dst
 
     def op(self, type, src, dst, src2=-1, relu=0, coff=0, shift=0):
         self.ops.append(dict(type=type, src=src, src2=src2, dst=dst, cin=0, cout=0, kh=0, kw=0, stride=0, pad=0,
-                             relu=int(relu), dst_coff=coff, shift=shift, wslot=-1))
+                             relu=int(relu), dst_coff=coff, shift=shift, wslot=-1, pair=0))
         return dst
 
 
@@ -351,9 +354,11 @@ class Trunk(nn.Module):
         """Enqueue the trunk on the current stream.  ``pooled``: fp32 tensor (or raw pointer) receiving the
         global-average-pooled feature per image with row stride ``pooled_ld`` floats."""
         _lib.require_device(images)
-        if images.dtype != torch.float32 or images.dim() != 4 or images.shape[1] != 3:
-            raise ValueError('images must be fp32 (B,3,H,W)')
-        images = images.contiguous()
+        if images.dim() != 4 or images.shape[1] != 3 or not images.is_floating_point():
+            raise ValueError('images must be a floating-point (B,3,H,W) tensor')
+        if images.shape[0] == 0:
+            raise ValueError('empty batch')
+        images = images.float().contiguous()
         B, _, H, W = images.shape
         self._ensure(images.device)
         ws = self._workspace(B, H, W, images.device)

@@ -38,6 +38,7 @@ struct specb200_trunk {
     std::vector<int> buf_ch;
     std::vector<ConvWeights> w;
     std::vector<int> wslot_cin;      // stored (padded) Cin of the op using the slot
+    std::vector<int> wslot_pair;     // slot belongs to a pixel-pair conv (weights expanded to 64 x 64)
     int out_buf = 0;
     int prec = PREC_BF16;
     int chunk = 0;
@@ -122,12 +123,18 @@ extern "C" int specb200_trunk_create(specb200_trunk_t** out, const specb200_op_t
     t->buf_ch.assign(buf_channels, buf_channels + n_bufs);
     t->w.resize(n_wslots);
     t->wslot_cin.assign(n_wslots, 0);
+    t->wslot_pair.assign(n_wslots, 0);
     t->out_buf = out_buf;
     t->prec = precision;
     for (const auto& o : t->ops) {
         if (o.type == SPECB200_OP_CONV) {
             if (o.wslot < 0 || o.wslot >= n_wslots) { set_error("trunk_create: bad wslot"); delete t; return 1; }
             t->wslot_cin[o.wslot] = o.cin;
+            const char* np = getenv("SPECB200_NO_PAIR");
+            const bool pair_ok = o.pair && t->prec != PREC_F32 && !(np && np[0] == '1') && o.cin == 32 && o.cout == 32 && o.kh == 3 &&
+                                 o.kw == 3 && o.stride == 1 && o.pad == 1 && o.dst_coff == 0 && t->buf_ch[o.src] == 32 &&
+                                 t->buf_ch[o.dst] == 32 && (o.src2 < 0 || t->buf_ch[o.src2] == 32);
+            t->wslot_pair[o.wslot] = pair_ok ? 1 : 0;
         }
     }
     {   // ResNet stem: dedicated kernel when op 0 is conv 7x7/2 pad 3 -> 64 (+ReLU) on the image and nothing else reads it
@@ -152,7 +159,31 @@ static void free_weights(ConvWeights& w) {
 extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const float* w_host, const float* b_host,
                                        int32_t cout, int32_t cin, int32_t kh, int32_t kw) {
     if (!t || wslot < 0 || wslot >= static_cast<int>(t->w.size()) || !w_host || !b_host) { set_error("set_conv: bad arguments"); return 1; }
-    const int cin_s = t->wslot_cin[wslot];           // stored Cin (>= cin, zero padded)
+    std::vector<float> pair_w, pair_b;
+    int cin_s = t->wslot_cin[wslot];                 // stored Cin (>= cin, zero padded)
+    if (t->wslot_pair[wslot]) {
+        // Pixel-pair view: [H][W][32] == [H][W/2][64].  Output pixel x = 2X + po reads input x + dx = 2(X + s) + pi with
+        // s = floor((po + dx) / 2), pi = (po + dx) mod 2, so the 32->32 3x3 conv is a 64->64 3x3 conv on the half-width
+        // grid whose weights are W2[po*32+co][pi*32+ci][kh][s+1] = w[co][ci][kh][dx+1] (half of them structurally zero).
+        if (cin != 32 || cout != 32 || kh != 3 || kw != 3) { set_error("set_conv: pair slot expects [32][32][3][3]"); return 1; }
+        pair_w.assign(static_cast<size_t>(64) * 64 * 9, 0.f);
+        pair_b.resize(64);
+        for (int po = 0; po < 2; ++po)
+            for (int co = 0; co < 32; ++co) {
+                pair_b[po * 32 + co] = b_host[co];
+                for (int ci = 0; ci < 32; ++ci)
+                    for (int y = 0; y < 3; ++y)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int q = po + dx;
+                            const int sft = (q < 0) ? -1 : (q >= 2 ? 1 : 0);
+                            const int pi = q - 2 * sft;
+                            pair_w[((static_cast<size_t>(po * 32 + co) * 64 + pi * 32 + ci) * 3 + y) * 3 + (sft + 1)] =
+                                w_host[((static_cast<size_t>(co) * 32 + ci) * 3 + y) * 3 + (dx + 1)];
+                        }
+            }
+        w_host = pair_w.data(); b_host = pair_b.data();
+        cout = 64; cin = 64; cin_s = 64;
+    }
     if (cin_s < cin) { set_error("set_conv: weight cin exceeds the op's cin"); return 1; }
     ConvWeights& w = t->w[wslot];
     free_weights(w);
@@ -281,7 +312,9 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
                 case SPECB200_OP_CONV: {
                     const ConvWeights& cw = t->w[o.wslot];
                     if (cw.bias == nullptr) { set_error("trunk_forward: conv weights for slot " + std::to_string(o.wslot) + " not set"); return 1; }
-                    if (cw.cout != o.cout || cw.kh != o.kh || cw.kw != o.kw) { set_error("trunk_forward: weight shape mismatch at op " + std::to_string(i)); return 1; }
+                    const bool pair = t->wslot_pair[o.wslot] != 0;
+                    if (cw.cout != (pair ? 64 : o.cout) || cw.kh != o.kh || cw.kw != o.kw) { set_error("trunk_forward: weight shape mismatch at op " + std::to_string(i)); return 1; }
+                    if (pair && ((sS.W & 1) || (dS.W & 1))) { set_error("trunk_forward: pixel-pair conv needs an even width (op " + std::to_string(i) + ")"); return 1; }
                     ConvParams p;
                     p.in = buf[o.src]; p.out = buf[o.dst]; p.res = o.src2 >= 0 ? buf[o.src2] : nullptr; p.bias = cw.bias;
                     p.N = nb; p.H = sS.H; p.W = sS.W; p.Cin = o.cin; p.Ho = dS.H; p.Wo = dS.W; p.Cout = o.cout;
@@ -293,6 +326,7 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
                     p.out_ld = t->buf_ch[o.dst]; p.out_coff = o.dst_coff;
                     p.res_ld = o.src2 >= 0 ? t->buf_ch[o.src2] : 0;
                     p.relu = o.relu;
+                    if (pair) { p.W /= 2; p.Wo /= 2; p.M /= 2; p.Cin = 64; p.Cout = 64; p.out_ld = 64; p.res_ld = o.src2 >= 0 ? 64 : 0; }
                     const bool ok = (t->prec == PREC_F32) ? conv_f32_launch(p, cw, s) : conv_tc_launch(p, cw, t->prec, s);
                     if (!ok) return 1;
                     break;

@@ -241,6 +241,8 @@ class HMR(nn.Module):
         _lib.require_device(images)
         dev = images.device
         B = images.shape[0]
+        if B == 0:
+            raise ValueError('empty batch')
         if self.use_cam or self.use_cam_feats:
             if cam_rotmat is None or cam_intrinsics is None or img_h is None:
                 raise ValueError('cam_rotmat, cam_intrinsics and img_h are required with use_cam / use_cam_feats')

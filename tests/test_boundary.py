@@ -27,7 +27,7 @@ def test_library_loads_and_exports_header_symbols():
 
 def test_struct_layouts_match_header():
     import ctypes
-    assert ctypes.sizeof(_lib.Op) == 14 * 4
+    assert ctypes.sizeof(_lib.Op) == 15 * 4
     assert ctypes.sizeof(_lib.HmrOutputs) == 8 * 16
     assert ctypes.sizeof(_lib.HmrParams) == 24 + 22 * 8
 

@@ -327,3 +327,103 @@ def test_batch_composition_invariance_at_full_size(models):
     R = out_big['pred_pose'].reshape(-1, 3, 3)
     assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3, device=R.device).expand_as(R), atol=1e-5)
     assert torch.isfinite(out_big['smpl_vertices']).all()
+
+
+# --------------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize('batch', [1, 33, 257])
+def test_ragged_batches_bf16(models, batch):
+    """Batch sizes that are not multiples of any tile (128-row GEMM tiles, 32-image SMPL tiles): image i of a ragged
+    batch equals image i of a padded batch bit for bit, and everything is finite."""
+    cc, _, hmr, _ = models
+    b = synthetic_batch(batch, seed=11)
+    got = _run_product(cc, hmr, b, 'bf16')
+    pad = 4 - batch % 4 if batch % 4 else 4
+    bp = {k: torch.cat([v, v[:pad]], 0) for k, v in b.items()}
+    ref = _run_product(cc, hmr, bp, 'bf16')
+    for k in got:
+        assert torch.isfinite(got[k]).all(), k
+        assert torch.equal(got[k], ref[k][:batch]), k
+
+
+def test_empty_batch_and_bad_inputs(models):
+    _, _, hmr, _ = models
+    hmr.to(DEV)
+    z = torch.zeros(0, 3, 224, 224, device=DEV)
+    with pytest.raises(ValueError):
+        hmr(z, torch.zeros(0, 3, 3, device=DEV), torch.zeros(0, 3, 3, device=DEV), torch.zeros(0, device=DEV),
+            torch.zeros(0, 2, device=DEV), torch.zeros(0, device=DEV), torch.zeros(0, device=DEV))
+    x = torch.randn(2, 3, 224, 224, device=DEV)
+    with pytest.raises(ValueError):
+        hmr(x)                                              # camera inputs are required with use_cam / use_cam_feats
+    with pytest.raises(ValueError):
+        hmr.backbone(torch.randn(2, 4, 224, 224, device=DEV))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        hmr.backbone(torch.randn(1, 3, 224, 224))
+
+
+def test_input_dtype_and_layout_are_normalised(models):
+    """fp16 / non-contiguous images are accepted like any nn.Module input and give the same result as fp32 contiguous."""
+    _, _, hmr, _ = models
+    hmr.backbone.set_precision('bf16')
+    hmr.to(DEV)
+    x = torch.randn(2, 224, 224, 3, device=DEV).half().float()      # values exactly representable in fp16
+    a = hmr.backbone.pooled_features(x.permute(0, 3, 1, 2).contiguous())
+    b = hmr.backbone.pooled_features(x.permute(0, 3, 1, 2))            # non-contiguous view
+    c = hmr.backbone.pooled_features(x.permute(0, 3, 1, 2).half())      # fp16 input
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_camcalib_full_resolution_fp32():
+    """The demo feeds CamCalib whole images at min-side 600 (camcalib_demo.py:95-102, pano_dataset.py:156-162)."""
+    cc, ref = make_camcalib_pair('resnet50', seed=1)
+    x = torch.randn(1, 3, 600, 800)
+    with torch.no_grad():
+        want = ref(x)
+    cc.backbone.set_precision('fp32')
+    got = cc.to(DEV)(x.to(DEV))
+    for g, w in zip(got, want):
+        _assert_close('logits 600x800', g, w, atol=5e-5, rtol=1e-4)
+    ang, R, K, f = cc.predict_camera(x.to(DEV), 600, 800)
+    wa = og.convert_preds_to_angles(*want)
+    _assert_close('angles', ang, torch.stack(wa, 1), atol=1e-5)
+    Rw, Kw, fw = og.cam_params_from_angles(*wa, 600, 800)
+    _assert_close('R', R, Rw, atol=1e-5)
+    _assert_close('K', K, Kw, atol=1e-2, rtol=1e-5)
+    assert float(K[0, 2, 2]) == 0.0                                      # cam_params.py:39-46 leaves K[2,2] = 0
+    cc.backbone.set_precision('bf16')
+    got16 = cc(x.to(DEV))
+    assert all(torch.isfinite(g).all() for g in got16)
+
+
+def test_use_cam_false_branch_fp32():
+    """HMR(use_cam=False): SMPLHead with fixed focal length and crop-normalised joints2d (hmr.py:70-74,114-121)."""
+    hmr, ref = make_pair('resnet34', seed=6, use_cam=False, use_cam_feats=False)
+    x = synthetic_batch(3, seed=6)['images']
+    with torch.no_grad():
+        want = ref(x)
+    hmr.backbone.set_precision('fp32')
+    got = hmr.to(DEV)(x.to(DEV))
+    assert list(got.keys()) == list(want.keys())
+    _assert_close('verts', got['smpl_vertices'], want['smpl_vertices'], atol=1e-3, rtol=1e-4)
+    _assert_close('pred_cam', got['pred_cam'], want['pred_cam'], atol=1e-5, rtol=1e-5)
+    _assert_close('cam_t', got['pred_cam_t'], want['pred_cam_t'], atol=1e-3, rtol=1e-4)
+    _assert_close('joints2d', got['smpl_joints2d'], want['smpl_joints2d'], atol=1e-3, rtol=1e-3)
+
+
+def test_reload_state_dict_repacks(models):
+    """load_state_dict after a forward marks the handles dirty: the next forward uses the new weights."""
+    cc, cc_ref, _, _ = models
+    cc.backbone.set_precision('fp32')
+    cc.to(DEV)
+    x = torch.randn(2, 3, 224, 224)
+    a = torch.cat(cc(x.to(DEV)), 1).clone()
+    sd = {k: v.clone() for k, v in cc.state_dict().items()}
+    sd2 = dict(sd)
+    sd2['fc_vfov.weight'] = sd['fc_vfov.weight'] * 0.5
+    sd2['backbone.layer4.2.bn3.weight'] = sd['backbone.layer4.2.bn3.weight'] * 1.5
+    cc.load_state_dict(sd2)
+    bnew = torch.cat(cc(x.to(DEV)), 1).clone()
+    assert not torch.allclose(a, bnew)
+    cc.load_state_dict(sd)
+    c = torch.cat(cc(x.to(DEV)), 1)
+    assert torch.equal(a, c)
