@@ -331,12 +331,13 @@ def run_ours(a):
     if rank == 0:
         # ---- roofline: per-op CUDA-event timing of both trunks (live, eager, on the launching stream)
         peaks = load_peaks()
-        conv_ms, conv_flops, step_ops_ms = 0.0, 0.0, 0.0
+        conv_ms, conv_flops, step_ops_ms, conv_bytes = 0.0, 0.0, 0.0, 0
         for m in (cc, hmr):
             m.backbone.profile_ops(b['images'])                   # warm
             rows = m.backbone.profile_ops(b['images'])
             conv_ms += sum(r['ms'] for r in rows if r['flops'] > 0)
             conv_flops += sum(r['flops'] for r in rows)
+            conv_bytes += sum(r.get('bytes', 0) for r in rows if r['flops'] > 0)
             step_ops_ms += sum(r['ms'] for r in rows)
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
         n_conv = sum(1 for m in (cc, hmr) for o in m.backbone._program.ops if o['type'] == 1)
@@ -359,7 +360,11 @@ def run_ours(a):
                     'steps': e2e_steps, 'how': 'pinned host inputs -> H2D -> SPECPipeline.forward_packed -> D2H of the packed records; copies on side streams, double-buffered'},
             'gpu_launches': int(launches_per_step * a.steps),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
-                         'frac': achieved / peaks['tf_sustained'], 'traffic': None,
+                         'frac': achieved / peaks['tf_sustained'],
+                         # dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step (2 trunks), from the
+                         # committed ncu --set full capture profiles/ncu_r01b.md (12.99 GB per trunk; resnet50, B=256, bf16)
+                         'traffic': 25.98e9 if (a.backbone == 'resnet50' and B == 256 and a.precision == 'bf16') else None,
+                         'algorithmic_bytes': conv_bytes,
                          'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)' % n_conv,
                          'how': 'sum of conv FLOPs of both trunks / sum of per-launch CUDA-event times (specb200_trunk_profile, eager, same stream)',
                          'peak_source': peaks['source'] + ' bf16 sustained', 'conv_ms_per_step': conv_ms,
