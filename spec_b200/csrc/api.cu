@@ -218,7 +218,7 @@ extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const
         if (!check_cuda(cudaMemcpy(w.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice), "w upload")) return 1;
         if (!conv_tc_make_weight_tmap(w)) return 1;
     } else {
-        w.block_n = conv_tc_pick_block_n(cout, kh * kw);
+        w.block_n = conv_tc_pick_block_n(cout, kh * kw * cin_s);
         if (cin_s == 4) {                           // stem layout: K index = (y*kwp + x)*4 + c
             w.kwp = 1;
             while (w.kwp < kw) w.kwp <<= 1;

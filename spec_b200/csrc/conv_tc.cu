@@ -391,7 +391,8 @@ constexpr int CONV_TCP_THREADS = 384;          // warps 0-3: TMA / MMA / TMEM / 
 template <int BLOCK_N, int STAGES>
 struct ConvTcpSmem {
     static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
-    static constexpr int EPI_BYTES = TILE_M * BLOCK_N * 2;
+    static constexpr int EPI_N = BLOCK_N < 128 ? BLOCK_N : 128;       // epilogue sub-tile width (columns)
+    static constexpr int EPI_BYTES = TILE_M * EPI_N * 2;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
     static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE_BYTES;
@@ -411,7 +412,9 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
     static_assert(A_MODE == A_TILED || A_MODE == A_IM2COL, "persistent kernel is TMA-fed");
     using L = ConvTcpSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = 2 * BLOCK_N;
-    constexpr int BOXES = BLOCK_N / 64;
+    constexpr int EPI_N = L::EPI_N;
+    constexpr int NSUB = BLOCK_N / EPI_N;                        // 128-column epilogue sub-tiles per accumulator
+    constexpr int BOXES = EPI_N / 64;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -520,75 +523,87 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
         const int t = q4 * 32 + lane;
         const bool leader = (warp == 4 && lane == 0);
         const uint32_t sw = static_cast<uint32_t>(t) & 7u;
-        auto issue_res = [&](int tile, uint32_t a) {
+        // epilogue work items are (tile, sub-tile h); staging buffer / residual barrier e = item & 1
+        auto issue_res = [&](int tile, int h, uint32_t e) {
             const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
-            mbar_arrive_expect_tx(bar_rfull + a * 8, L::EPI_BYTES);
+            mbar_arrive_expect_tx(bar_rfull + e * 8, L::EPI_BYTES);
 #pragma unroll
             for (int bx = 0; bx < BOXES; ++bx)
-                tma_load_2d(e_base + a * L::EPI_BYTES + bx * (TILE_M * 128), &maps.res, bar_rfull + a * 8,
-                            n_tile * BLOCK_N + bx * 64, m_tile * TILE_M);
+                tma_load_2d(e_base + e * L::EPI_BYTES + bx * (TILE_M * 128), &maps.res, bar_rfull + e * 8,
+                            n_tile * BLOCK_N + h * EPI_N + bx * 64, m_tile * TILE_M);
         };
-        if (leader && has_res && static_cast<int>(blockIdx.x) < total_tiles) issue_res(blockIdx.x, 0);
-        uint32_t tc = 0;
+        if (leader && has_res && static_cast<int>(blockIdx.x) < total_tiles) issue_res(blockIdx.x, 0, 0);
+        uint32_t tc = 0, ec = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
             const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
             const int n0 = n_tile * BLOCK_N;
-            if (leader) {
-                tma_store_wait_read0();                            // store of tile tc-1 has finished reading buffer a^1
-                const int next = tile + gridDim.x;
-                if (has_res && next < total_tiles) issue_res(next, a ^ 1);
-            }
-            mbar_wait(bar_tfull + a * 8, aph);
-            tc_fence_after();
-            if (has_res) mbar_wait(bar_rfull + a * 8, aph);
-            const uint32_t row_addr = e_base + a * L::EPI_BYTES + static_cast<uint32_t>(t) * 128u;
-            const uint32_t tmem_acc = tmem_base + a * BLOCK_N + (static_cast<uint32_t>(q4 * 32) << 16);
 #pragma unroll 1
-            for (int c = grp * (BLOCK_N / 64); c < (grp + 1) * (BLOCK_N / 64); ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_acc + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int col = c * 32 + q * 8;
-                    const uint32_t addr = row_addr + (col >> 6) * (TILE_M * 128) + ((((col & 63) >> 3) ^ sw) << 4);
-                    float f[8];
-                    const float4 b0 = *reinterpret_cast<const float4*>(sbias + n0 + col);
-                    const float4 b1 = *reinterpret_cast<const float4*>(sbias + n0 + col + 4);
-                    f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
-                    f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
-                    f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
-                    f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
+            for (int h = 0; h < NSUB; ++h, ++ec) {
+                const uint32_t e = ec & 1, eph = (ec >> 1) & 1;
+                if (leader) {
+                    tma_store_wait_read0();                        // the previous item's store has finished reading buffer e^1
                     if (has_res) {
-                        uint32_t ru[4];
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ru[0]), "=r"(ru[1]), "=r"(ru[2]), "=r"(ru[3]) : "r"(addr));
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 rf = DT<T>::unpack2(ru[e]);
-                            f[2 * e] += rf.x;
-                            f[2 * e + 1] += rf.y;
-                        }
+                        if (h + 1 < NSUB) issue_res(tile, h + 1, e ^ 1);
+                        else if (tile + static_cast<int>(gridDim.x) < total_tiles) issue_res(tile + gridDim.x, 0, e ^ 1);
                     }
-                    if (p.relu) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-                    }
-                    const uint32_t o0 = DT<T>::pack2(f[0], f[1]), o1 = DT<T>::pack2(f[2], f[3]);
-                    const uint32_t o2 = DT<T>::pack2(f[4], f[5]), o3 = DT<T>::pack2(f[6], f[7]);
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + a * 8);        // accumulator a may be overwritten
-            fence_proxy_async_smem();
-            named_bar_sync(1, 256);
-            if (leader) {
+                if (h == 0) {
+                    mbar_wait(bar_tfull + a * 8, aph);
+                    tc_fence_after();
+                }
+                if (has_res) mbar_wait(bar_rfull + e * 8, eph);
+                const uint32_t row_addr = e_base + e * L::EPI_BYTES + static_cast<uint32_t>(t) * 128u;
+                const uint32_t tmem_acc = tmem_base + a * BLOCK_N + h * EPI_N + (static_cast<uint32_t>(q4 * 32) << 16);
+#pragma unroll 1
+                for (int c = grp * (EPI_N / 64); c < (grp + 1) * (EPI_N / 64); ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_acc + c * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int bx = 0; bx < BOXES; ++bx)
-                    tma_store_2d(&maps.out, e_base + a * L::EPI_BYTES + bx * (TILE_M * 128), p.out_coff + n0 + bx * 64, m_tile * TILE_M);
-                tma_store_commit();
+                    for (int q = 0; q < 4; ++q) {
+                        const int col = c * 32 + q * 8;
+                        const uint32_t addr = row_addr + (col >> 6) * (TILE_M * 128) + ((((col & 63) >> 3) ^ sw) << 4);
+                        float f[8];
+                        const float4 b0 = *reinterpret_cast<const float4*>(sbias + n0 + h * EPI_N + col);
+                        const float4 b1 = *reinterpret_cast<const float4*>(sbias + n0 + h * EPI_N + col + 4);
+                        f[0] = __uint_as_float(v[q * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[q * 8 + 1]) + b0.y;
+                        f[2] = __uint_as_float(v[q * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[q * 8 + 3]) + b0.w;
+                        f[4] = __uint_as_float(v[q * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[q * 8 + 5]) + b1.y;
+                        f[6] = __uint_as_float(v[q * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[q * 8 + 7]) + b1.w;
+                        if (has_res) {
+                            uint32_t ru[4];
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ru[0]), "=r"(ru[1]), "=r"(ru[2]), "=r"(ru[3]) : "r"(addr));
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                const float2 rf = DT<T>::unpack2(ru[x]);
+                                f[2 * x] += rf.x;
+                                f[2 * x + 1] += rf.y;
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int x = 0; x < 8; ++x) f[x] = fmaxf(f[x], 0.f);
+                        }
+                        const uint32_t o0 = DT<T>::pack2(f[0], f[1]), o1 = DT<T>::pack2(f[2], f[3]);
+                        const uint32_t o2 = DT<T>::pack2(f[4], f[5]), o3 = DT<T>::pack2(f[6], f[7]);
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                    }
+                }
+                if (h == NSUB - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + a * 8);    // accumulator a may be overwritten
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 256);
+                if (leader) {
+#pragma unroll
+                    for (int bx = 0; bx < BOXES; ++bx)
+                        tma_store_2d(&maps.out, e_base + e * L::EPI_BYTES + bx * (TILE_M * 128),
+                                     p.out_coff + n0 + h * EPI_N + bx * 64, m_tile * TILE_M);
+                    tma_store_commit();
+                }
             }
         }
         if (leader) tma_store_wait_read0();
@@ -663,10 +678,12 @@ static bool make_tmap_im2col(CUtensorMap* m, const ConvParams& p) {
     return true;
 }
 
-int conv_tc_pick_block_n(int cout, int taps) {
+int conv_tc_pick_block_n(int cout, int K) {
     if (cout <= 32) return 32;
     if (cout <= 64) return 64;
-    if (taps > 1 && cout >= 256 && (cout % 256) == 0) {
+    // 128 x 256 tiles when there are >= 4 k-blocks to amortise the wider epilogue (measured: K = 64 / 128 expansions
+    // are faster at N = 128, everything with K >= 256 and Cout % 256 == 0 is faster at N = 256)
+    if (cout >= 256 && (cout % 256) == 0 && K >= 256) {
         const char* e = getenv("SPECB200_NO_N256");
         if (!(e && e[0] == '1')) return 256;
     }
@@ -733,10 +750,12 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
             !make_tmap_2d(&maps.res, p.res, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.res_ld), static_cast<uint64_t>(p.res_ld), TILE_M)) return false;
     }
     if (g_no_persist < 0) { const char* e = getenv("SPECB200_NO_PERSIST"); g_no_persist = (e && e[0] == '1') ? 1 : 0; }
-    if constexpr (BLOCK_N == 64 || BLOCK_N == 128) {
-        const bool mma_bound = p.kh * p.kw > 1;                  // measured: two co-resident one-tile CTAs feed the tensor pipe better
-        if (!g_no_persist && !mma_bound && (mode == A_TILED || mode == A_IM2COL) && (p.Cout & 63) == 0 && p.Cout <= 2048)
-            return launch_persistent<T, BLOCK_N, (BLOCK_N == 128 ? 4 : 6)>(p, maps, mode, m_tiles, n_tiles, s);
+    if constexpr (BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256) {
+        // k>1 convs at N<=128: two co-resident one-tile CTAs feed the tensor pipe better than one persistent CTA (measured);
+        // at N=256 the operand bytes per MMA cycle drop to 96 B and the persistent kernel (overlapped epilogue) wins.
+        const bool one_tile_better = p.kh * p.kw > 1 && BLOCK_N < 256;
+        if (!g_no_persist && !one_tile_better && (mode == A_TILED || mode == A_IM2COL) && (p.Cout & 63) == 0 && p.Cout <= 2048)
+            return launch_persistent<T, BLOCK_N, (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6))>(p, maps, mode, m_tiles, n_tiles, s);
     }
     auto k0 = conv_tc_kernel<T, BLOCK_N, STAGES, A_TILED>;
     auto k1 = conv_tc_kernel<T, BLOCK_N, STAGES, A_IM2COL>;

@@ -44,7 +44,7 @@ bool check_cuda(cudaError_t e, const char* what);
 // tcgen05 implicit-GEMM conv (conv_tc.cu).  prec is PREC_BF16 or PREC_F16.
 bool conv_tc_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s);
 bool conv_tc_make_weight_tmap(ConvWeights& w);
-int conv_tc_pick_block_n(int cout, int taps);
+int conv_tc_pick_block_n(int cout, int K);
 
 // dedicated 7x7/2 stem (conv_stem.cu): reads the fp32 NCHW image directly, writes NHWC 16-bit [N,Ho,Wo,64]
 bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N, int H, int W, int Ho, int Wo, int prec,
