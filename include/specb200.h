@@ -160,6 +160,23 @@ int specb200_hmrtail_forward(specb200_hmrtail_t* t, int32_t batch, void* workspa
 int64_t specb200_hmrtail_last_launches(specb200_hmrtail_t* t);
 void specb200_hmrtail_destroy(specb200_hmrtail_t* t);
 
+/* ---- eval-side metrics on the device: replaces the J_regressor_h36m matmul, pelvis centring, MPJPE,
+ *      numpy Procrustes (PA-MPJPE) and per-vertex error of /root/reference/spec/trainer.py:272-316 and
+ *      /root/reference/spec/utils/compute_error.py:33-86 -------------------------------------------------------------- */
+typedef struct specb200_eval specb200_eval_t;
+/* J_regressor_h36m_host: [17][6890] fp32; joint_mapper14_host: 14 indices into the 17 joints (constants.py:109-111). */
+int specb200_eval_create(specb200_eval_t** out, const float* J_regressor_h36m_host, const int32_t* joint_mapper14_host);
+int64_t specb200_eval_workspace_bytes(specb200_eval_t* t, int32_t batch);
+/* pred_verts_dev: [batch][6890][3] with per-image stride ld_pred floats.  Ground truth: either gt_keypoints14_dev
+ * ([batch][14][3], already root-centred, trainer.py:274) or gt_verts_dev (joints regressed and centred like
+ * compute_error.py:49-57).  Outputs (device, fp32): mpjpe[batch], pampjpe[batch], v2v[batch] (NULL to skip; needs
+ * gt_verts; center_v2v = 1 subtracts the pelvis of each mesh first, compute_error.py:64-68), pred_keypoints14 (NULL ok). */
+int specb200_eval_forward(specb200_eval_t* t, int32_t batch, const float* pred_verts_dev, int64_t ld_pred,
+                          const float* gt_keypoints14_dev, const float* gt_verts_dev, int64_t ld_gt, int32_t center_v2v,
+                          void* workspace_dev, int64_t workspace_bytes, float* mpjpe_dev, float* pampjpe_dev, float* v2v_dev,
+                          float* pred_keypoints14_dev, void* stream);
+void specb200_eval_destroy(specb200_eval_t* t);
+
 /* ---- standalone ops (unit tests / building blocks) -------------------------------------------- */
 /* out[m][n] = sum_k a[m][k] w[n][k] + bias[n] ; fp32 */
 int specb200_linear_f32(const float* a_dev, int32_t lda, const float* w_dev, int32_t ldw, const float* bias_dev,

@@ -12,8 +12,9 @@ from .hmr import HMR, HMRHead, SMPLCamHead, SMPLHead
 from .backbone import get_backbone_info, resnet18, resnet34, resnet50, resnet101, hrnet_w32, hrnet_w48
 from .cam_utils import convert_preds_to_angles, decode_logits
 from .pipeline import SPECPipeline, unpack_record, all_gather_records, shard_range
+from .metrics import EvalMetrics
 
 __all__ = ['CameraRegressorNetwork', 'HMR', 'HMRHead', 'SMPLCamHead', 'SMPLHead', 'get_backbone_info',
            'resnet18', 'resnet34', 'resnet50', 'resnet101', 'hrnet_w32', 'hrnet_w48',
            'convert_preds_to_angles', 'decode_logits', 'SPECPipeline', 'unpack_record', 'all_gather_records',
-           'shard_range']
+           'shard_range', 'EvalMetrics']

@@ -78,6 +78,11 @@ _PROTOS = {
                                            C.c_void_p]),
     'specb200_hmrtail_last_launches': (C.c_int64, [C.c_void_p]),
     'specb200_hmrtail_destroy': (None, [C.c_void_p]),
+    'specb200_eval_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    'specb200_eval_workspace_bytes': (C.c_int64, [C.c_void_p, C.c_int32]),
+    'specb200_eval_forward': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'specb200_eval_destroy': (None, [C.c_void_p]),
     'specb200_linear_f32': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }

@@ -673,3 +673,40 @@ extern "C" int specb200_linear_f32(const float* a, int32_t lda, const float* w, 
                                    int32_t ldo, int32_t m, int32_t n, int32_t k, void* stream) {
     return linear_f32_launch(a, lda, w, ldw, bias, nullptr, 0, out, ldo, m, n, k, static_cast<cudaStream_t>(stream)) ? 0 : 1;
 }
+
+// =============================================================================================== eval metrics
+struct specb200_eval { float* JT = nullptr; int* map14 = nullptr; };
+
+extern "C" int specb200_eval_create(specb200_eval_t** out, const float* J_host, const int32_t* map_host) {
+    if (!out || !J_host || !map_host) { set_error("eval_create: bad arguments"); return 1; }
+    for (int i = 0; i < 14; ++i) if (map_host[i] < 0 || map_host[i] >= 17) { set_error("eval_create: joint mapper out of range"); return 1; }
+    specb200_eval* t = new specb200_eval();
+    std::vector<float> JT(static_cast<size_t>(SMPL_NV) * 20, 0.f);
+    for (int j = 0; j < 17; ++j)
+        for (int v = 0; v < SMPL_NV; ++v) JT[static_cast<size_t>(v) * 20 + j] = J_host[static_cast<size_t>(j) * SMPL_NV + v];
+    bool ok = upload(&t->JT, JT);
+    ok = ok && check_cuda(cudaMalloc(&t->map14, 14 * sizeof(int)), "cudaMalloc") &&
+         check_cuda(cudaMemcpy(t->map14, map_host, 14 * sizeof(int), cudaMemcpyHostToDevice), "upload");
+    if (!ok) { specb200_eval_destroy(t); return 1; }
+    *out = t;
+    return 0;
+}
+extern "C" int64_t specb200_eval_workspace_bytes(specb200_eval_t* t, int32_t batch) {
+    if (!t || batch <= 0) { set_error("eval_workspace_bytes: bad arguments"); return -1; }
+    return static_cast<int64_t>(sizeof(float)) * (static_cast<int64_t>(2) * batch * 51 + static_cast<int64_t>(2) * batch * 3) + 256;
+}
+extern "C" int specb200_eval_forward(specb200_eval_t* t, int32_t B, const float* pred_verts, int64_t ld_pred, const float* gt_kp14,
+                                     const float* gt_verts, int64_t ld_gt, int32_t center_v2v, void* ws, int64_t ws_bytes,
+                                     float* mpjpe, float* pampjpe, float* v2v, float* pred_kp14, void* stream) {
+    if (!t || B <= 0 || !pred_verts || !ws || !mpjpe || !pampjpe) { set_error("eval_forward: bad arguments"); return 1; }
+    if (ws_bytes < specb200_eval_workspace_bytes(t, B)) { set_error("eval_forward: workspace too small"); return 1; }
+    float* w = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ws), 16));
+    return eval_launch(t->JT, t->map14, B, pred_verts, ld_pred, gt_kp14, gt_verts, ld_gt, center_v2v, w, mpjpe, pampjpe, v2v, pred_kp14,
+                       static_cast<cudaStream_t>(stream)) ? 0 : 1;
+}
+extern "C" void specb200_eval_destroy(specb200_eval_t* t) {
+    if (!t) return;
+    if (t->JT) cudaFree(t->JT);
+    if (t->map14) cudaFree(t->map14);
+    delete t;
+}

@@ -58,6 +58,11 @@ bool linear_f32_launch(const float* A, int lda, const float* W, int ldw, const f
                        int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s, int ksplit = 1,
                        size_t split_stride = 0);
 
+// eval-side metrics (eval.cu)
+bool eval_launch(const float* JT, const int* map14, int B, const float* pred_verts, long long ld_pred, const float* gt_kp14,
+                 const float* gt_verts, long long ld_gt, int center_v2v, float* ws, float* mpjpe, float* pampjpe, float* v2v,
+                 float* pred_kp14, cudaStream_t s);
+
 // elementwise / layout kernels (elementwise.cu)
 bool images_to_nhwc_launch(const float* img_nchw, void* out_nhwc, int N, int H, int W, int cpad, int prec, cudaStream_t s);
 bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int prec, cudaStream_t s);

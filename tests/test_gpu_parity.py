@@ -427,3 +427,45 @@ def test_reload_state_dict_repacks(models):
     cc.load_state_dict(sd)
     c = torch.cat(cc(x.to(DEV)), 1)
     assert torch.equal(a, c)
+
+
+# --------------------------------------------------------------------------------------- eval metrics
+def test_eval_metrics_match_oracle():
+    from oracle import eval_metrics as oe
+    from spec_b200.metrics import EvalMetrics
+    rng = np.random.RandomState(3)
+    J = rng.rand(17, 6890).astype(np.float64) ** 8
+    J = (J / J.sum(1, keepdims=True)).astype(np.float32)
+    Jt = torch.from_numpy(J)
+    B = 37
+    gt_v = torch.from_numpy((rng.randn(B, 6890, 3) * 0.3).astype(np.float32))
+    # prediction = rotated / scaled / shifted / noisy ground truth, so Procrustes has real work to do
+    ang = 0.4
+    Rz = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], dtype=torch.float32)
+    pred_v = (1.1 * gt_v @ Rz.T + torch.tensor([0.05, -0.02, 0.1]) + 0.01 * torch.randn(B, 6890, 3, generator=torch.Generator().manual_seed(0)))
+    gt_kp = (torch.matmul(Jt[None].expand(B, -1, -1), gt_v))
+    gt_kp = gt_kp[:, oe.H36M_TO_J14] - gt_kp[:, [0]]
+    m = EvalMetrics(J).to(DEV)
+    # trainer style: gt keypoints given, raw v2v
+    got = m(pred_v.to(DEV), gt_keypoints_3d=gt_kp.to(DEV), gt_vertices=gt_v.to(DEV))
+    mp, pa, v2v, pk = oe.trainer_metrics(pred_v, gt_kp, Jt, gt_v)
+    _assert_close('mpjpe', got['mpjpe'], torch.from_numpy(mp), atol=1e-5, rtol=1e-4)
+    _assert_close('pa_mpjpe', got['pa_mpjpe'], torch.from_numpy(pa), atol=2e-5, rtol=1e-3)
+    _assert_close('v2v', got['v2v'], torch.from_numpy(v2v), atol=1e-5, rtol=1e-4)
+    _assert_close('pred_kp', got['pred_keypoints_3d'], pk, atol=1e-5)
+    # compute_error.py style: joints regressed from both meshes, centred v2v
+    got = m(pred_v.to(DEV), gt_vertices=gt_v.to(DEV), center_v2v=True)
+    mp, pa, v2v = oe.eval_single(pred_v, gt_v, Jt)
+    _assert_close('mpjpe2', got['mpjpe'], torch.from_numpy(mp), atol=1e-5, rtol=1e-4)
+    _assert_close('pa_mpjpe2', got['pa_mpjpe'], torch.from_numpy(pa), atol=2e-5, rtol=1e-3)
+    _assert_close('v2v2', got['v2v'], torch.from_numpy(v2v), atol=1e-5, rtol=1e-4)
+    # a reflected prediction exercises the det(U V^T) < 0 branch
+    refl = pred_v * torch.tensor([-1.0, 1.0, 1.0])
+    got = m(refl.to(DEV), gt_keypoints_3d=gt_kp.to(DEV))
+    _, pa, _, _ = oe.trainer_metrics(refl, gt_kp, Jt)
+    _assert_close('pa_mpjpe reflected', got['pa_mpjpe'], torch.from_numpy(pa), atol=5e-5, rtol=2e-3)
+    # works straight on the strided vertices view of a packed record buffer
+    rec = torch.zeros(B, sb.pipeline.RECORD_FLOATS, device=DEV)
+    sb.unpack_record(rec)['smpl_vertices'].copy_(pred_v.to(DEV))
+    got2 = m(sb.unpack_record(rec)['smpl_vertices'], gt_keypoints_3d=gt_kp.to(DEV))
+    assert torch.equal(got2['mpjpe'], m(pred_v.to(DEV), gt_keypoints_3d=gt_kp.to(DEV))['mpjpe'])

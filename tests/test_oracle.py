@@ -115,3 +115,18 @@ def test_golden_vectors_reproduce():
     out = build_case()
     for k in g.files:
         np.testing.assert_allclose(out[k], g[k], rtol=0, atol=1e-5, err_msg=k)
+
+
+def test_procrustes_oracle_invariants():
+    """reconstruction_error is invariant to a similarity transform of the prediction (and zero for an exact one)."""
+    from oracle.eval_metrics import reconstruction_error
+    rng = np.random.RandomState(0)
+    S2 = rng.randn(5, 14, 3).astype(np.float32)
+    q, _ = np.linalg.qr(rng.randn(3, 3))
+    if np.linalg.det(q) < 0:
+        q[:, 0] *= -1
+    S1 = (1.7 * S2 @ q.T + np.array([0.3, -2.0, 1.0])).astype(np.float32)
+    assert reconstruction_error(S1, S2).max() < 1e-5
+    noisy = S1 + 0.05 * rng.randn(*S1.shape).astype(np.float32)
+    e = reconstruction_error(noisy, S2)
+    assert (e > 1e-3).all() and (e < 0.2).all()
