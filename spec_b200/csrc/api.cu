@@ -327,7 +327,8 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
                     p.res_ld = o.src2 >= 0 ? t->buf_ch[o.src2] : 0;
                     p.relu = o.relu;
                     if (pair) { p.W /= 2; p.Wo /= 2; p.M /= 2; p.Cin = 64; p.Cout = 64; p.out_ld = 64; p.res_ld = o.src2 >= 0 ? 64 : 0; }
-                    const bool ok = (t->prec == PREC_F32) ? conv_f32_launch(p, cw, s) : conv_tc_launch(p, cw, t->prec, s);
+                    const bool ok = (t->prec == PREC_F32) ? conv_f32_launch(p, cw, s)
+                                    : (conv_halo_applicable(p, cw) ? conv_halo_launch(p, cw, t->prec, s) : conv_tc_launch(p, cw, t->prec, s));
                     if (!ok) return 1;
                     break;
                 }

@@ -46,6 +46,10 @@ bool conv_tc_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStr
 bool conv_tc_make_weight_tmap(ConvWeights& w);
 int conv_tc_pick_block_n(int cout, int K);
 
+// 3x3/1 conv with on-chip halo reuse (conv_halo.cu)
+bool conv_halo_applicable(const ConvParams& p, const ConvWeights& w);
+bool conv_halo_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s);
+
 // dedicated 7x7/2 stem (conv_stem.cu): reads the fp32 NCHW image directly, writes NHWC 16-bit [N,Ho,Wo,64]
 bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N, int H, int W, int Ho, int Wo, int prec,
                        cudaStream_t s);

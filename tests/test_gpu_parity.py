@@ -75,11 +75,15 @@ CONV_CASES = [
     (64, 256, 1, 2, 0, False, 14, 14, 2),           # strided 1x1 (downsample) -> gather path
     (32, 32, 3, 1, 1, True, 10, 10, 2),             # Cin=32 (HRNet): two taps per k-block, BLOCK_N=32
     (64, 512, 1, 1, 0, False, 7, 7, 5),             # 4 N tiles
+    (64, 64, 3, 1, 1, True, 9, 23, 3),              # halo kernel, resident weights, ragged 8x14 tiles, residual
+    (128, 128, 3, 1, 1, True, 20, 30, 2),           # halo kernel, streamed weights (2 channel blocks), residual
+    (256, 256, 3, 1, 1, False, 16, 17, 1),          # halo kernel, N=256 (two epilogue sub-tiles), 4 channel blocks
+    (256, 512, 1, 1, 0, True, 9, 9, 3),             # persistent 1x1, N=256 tiles, residual
 ]
 
 
 @pytest.mark.parametrize('precision', ['bf16', 'fp16', 'fp32'])
-@pytest.mark.parametrize('case', CONV_CASES, ids=[f'c{c[0]}-{c[1]}k{c[2]}s{c[3]}' for c in CONV_CASES])
+@pytest.mark.parametrize('case', CONV_CASES, ids=[f'c{c[0]}-{c[1]}k{c[2]}s{c[3]}h{c[6]}' for c in CONV_CASES])
 def test_conv_kernels(case, precision):
     cmid, cout, k, stride, pad, res, H, W, B = case
     t = _mini(cmid, cout, k, stride, pad, res, precision)
