@@ -617,6 +617,8 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
     }
 }
 
+#include "conv_tc2.cuh"
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -702,6 +704,36 @@ static int g_force_gather = -1;     // SPECB200_FORCE_GATHER=1 disables the TMA 
 static int g_no_persist = -1;       // SPECB200_NO_PERSIST=1 keeps the one-tile-per-CTA kernel (A-B test)
 static int g_num_sms = 0;
 
+static int g_use_2cta = -1;         // SPECB200_NO_2CTA=1 keeps the one-CTA persistent kernel
+
+// CTA-pair (cta_group::2) persistent kernel: 256 x BLOCK_N tiles over clusters of two CTAs
+template <typename T, int BLOCK_N, int STAGES>
+static bool launch_pair(const ConvParams& p, ConvTcMaps maps, const ConvWeights& w, int mode, int m_tiles, int n_tiles, cudaStream_t s) {
+    using L = ConvTc2Smem<BLOCK_N, STAGES>;
+    // each CTA loads HALF of the weight tile: box of BLOCK_N/2 rows
+    if (!make_tmap_2d(&maps.b, w.w_tc, static_cast<uint64_t>(w.cout_pad), static_cast<uint64_t>(w.K_pad), static_cast<uint64_t>(w.K_pad), BLOCK_N / 2)) return false;
+    auto k0 = conv_tcp2_kernel<T, BLOCK_N, STAGES, A_TILED>;
+    auto k1 = conv_tcp2_kernel<T, BLOCK_N, STAGES, A_IM2COL>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (!check_cuda(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        if (!check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
+        attr_done = true;
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!check_cuda(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev), "sm count")) return false;
+    }
+    const long long total = static_cast<long long>((m_tiles + 1) / 2) * n_tiles;       // pair tiles
+    if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles"); return false; }
+    const long long pairs = g_num_sms / 2;
+    const unsigned grid = 2u * static_cast<unsigned>(total < pairs ? total : pairs);
+    if (mode == A_TILED) k0<<<grid, CONV_TCP_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles, static_cast<int>(total));
+    else k1<<<grid, CONV_TCP_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles, static_cast<int>(total));
+    return check_cuda(cudaGetLastError(), "conv_tcp2 launch");
+}
+
 template <typename T, int BLOCK_N, int STAGES>
 static bool launch_persistent(const ConvParams& p, const ConvTcMaps& maps, int mode, int m_tiles, int n_tiles, cudaStream_t s) {
     using L = ConvTcpSmem<BLOCK_N, STAGES>;
@@ -754,8 +786,13 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
         // k>1 convs at N<=128: two co-resident one-tile CTAs feed the tensor pipe better than one persistent CTA (measured);
         // at N=256 the operand bytes per MMA cycle drop to 96 B and the persistent kernel (overlapped epilogue) wins.
         const bool one_tile_better = p.kh * p.kw > 1 && BLOCK_N < 256;
-        if (!g_no_persist && !one_tile_better && (mode == A_TILED || mode == A_IM2COL) && (p.Cout & 63) == 0 && p.Cout <= 2048)
+        if (!g_no_persist && !one_tile_better && (mode == A_TILED || mode == A_IM2COL) && (p.Cout & 63) == 0 && p.Cout <= 2048) {
+            if (g_use_2cta < 0) { const char* e = getenv("SPECB200_NO_2CTA"); g_use_2cta = (e && e[0] == '1') ? 0 : 1; }
+            if constexpr (BLOCK_N == 256) {
+                if (g_use_2cta && m_tiles >= 2) return launch_pair<T, 256, 4>(p, maps, w, mode, m_tiles, n_tiles, s);
+            }
             return launch_persistent<T, BLOCK_N, (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6))>(p, maps, mode, m_tiles, n_tiles, s);
+        }
     }
     auto k0 = conv_tc_kernel<T, BLOCK_N, STAGES, A_TILED>;
     auto k1 = conv_tc_kernel<T, BLOCK_N, STAGES, A_IM2COL>;
