@@ -365,7 +365,7 @@ def run_ours(a):
                          # committed ncu --set full capture profiles/ncu_r01b.md (12.99 GB per trunk; resnet50, B=256, bf16)
                          'traffic': 25.98e9 if (a.backbone == 'resnet50' and B == 256 and a.precision == 'bf16') else None,
                          'algorithmic_bytes': conv_bytes,
-                         'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)' % n_conv,
+                         'kernel': 'tcgen05 implicit-GEMM conv family: conv_tcp/conv_tcp2 (cta_group::2)/conv_tc/conv3x3_halo/conv_stem7, %d launches/step' % n_conv,
                          'how': 'sum of conv FLOPs of both trunks / sum of per-launch CUDA-event times (specb200_trunk_profile, eager, same stream)',
                          'peak_source': peaks['source'] + ' bf16 sustained', 'conv_ms_per_step': conv_ms,
                          'conv_share_of_trunk_ops': conv_ms / step_ops_ms if step_ops_ms else None,
