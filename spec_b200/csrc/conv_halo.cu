@@ -20,19 +20,27 @@
 
 namespace sb {
 
-constexpr int HL_TH = 8, HL_TW = 14, HL_PW = 16;          // output tile rows / cols, padded pitch
-constexpr int HL_PATCH_ROWS = (HL_TH + 2) * HL_PW;         // 160 pixels loaded per channel block
-constexpr int HL_PATCH_TX = HL_PATCH_ROWS * 128;           // 20480 bytes per TMA load
-constexpr int HL_PATCH_BYTES = 21504;                      // slot size: 168 rows (taps read up to row 161), 1024-aligned
+// Tile geometry (TH output rows x TW = PW-2 output cols on a padded grid of pitch PW, TH*PW = 128 GEMM rows):
+//   G = 0:  8 x 14 (pitch 16)  -- narrow maps (W = 14)          G = 1:  4 x 30 (pitch 32)  -- W >= 28 (93.75 % of the rows useful)
+template <int G> struct HaloGeom;
+template <> struct HaloGeom<0> { static constexpr int TH = 8, PW = 16; };
+template <> struct HaloGeom<1> { static constexpr int TH = 4, PW = 32; };
+template <int G> struct HaloDims {
+    static constexpr int TH = HaloGeom<G>::TH, PW = HaloGeom<G>::PW, TW = PW - 2;
+    static constexpr int PATCH_ROWS = (TH + 2) * PW;               // pixels loaded per channel block
+    static constexpr int PATCH_TX = PATCH_ROWS * 128;              // bytes per TMA load
+    static constexpr int PATCH_BYTES = ((128 + 2 * PW + 2) * 128 + 1023) / 1024 * 1024;   // slot: taps read up to row 127 + 2*PW + 2
+    static constexpr int PW_SHIFT = (PW == 16) ? 4 : 5;
+};
 constexpr int HL_THREADS = 384;
 
-template <int BLOCK_N, int PA, int PB>
+template <int BLOCK_N, int PA, int PB, int G>
 struct HaloSmem {
     static constexpr int B_SLOT = BLOCK_N * 128;
     static constexpr int EPI_N = BLOCK_N < 128 ? BLOCK_N : 128;
     static constexpr int EPI_BYTES = 128 * EPI_N * 2;       // per sub-tile: EPI_N/64 boxes of 128 rows x 128 B (112 rows used)
     static constexpr int A_OFF = 0;
-    static constexpr int B_OFF = PA * HL_PATCH_BYTES;
+    static constexpr int B_OFF = PA * HaloDims<G>::PATCH_BYTES;
     static constexpr int EPI_OFF = B_OFF + PB * B_SLOT;
     static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BYTES;  // a_full[PA] a_empty[PA] b_full[PB] b_empty[PB] tfull[2] tempty[2] rfull[2]
     static constexpr int NBAR = 2 * PA + 2 * PB + 6;
@@ -51,11 +59,13 @@ struct HaloMaps {
     CUtensorMap res;    // residual, same box
 };
 
-template <typename T, int BLOCK_N, int PA, int PB, bool B_RESIDENT>
+template <typename T, int BLOCK_N, int PA, int PB, bool B_RESIDENT, int G>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv3x3_halo_kernel(const ConvParams p, const __grid_constant__ HaloMaps maps, int tiles_w, int tiles_h, int total_tiles)
 {
-    using L = HaloSmem<BLOCK_N, PA, PB>;
+    using L = HaloSmem<BLOCK_N, PA, PB, G>;
+    using D = HaloDims<G>;
+    constexpr int HL_TH = D::TH, HL_TW = D::TW, HL_PW = D::PW, HL_PATCH_TX = D::PATCH_TX, HL_PATCH_BYTES = D::PATCH_BYTES;
     constexpr int TMEM_COLS = 2 * BLOCK_N;
     constexpr int EPI_N = L::EPI_N;
     constexpr int NSUB = BLOCK_N / EPI_N;
@@ -173,7 +183,7 @@ conv3x3_halo_kernel(const ConvParams p, const __grid_constant__ HaloMaps maps, i
         const int q4 = warp & 3;
         const int grp = (warp - 4) >> 2;
         const int q = q4 * 32 + lane;
-        const int r = q >> 4, c = q & 15;
+        const int r = q >> D::PW_SHIFT, c = q & (HL_PW - 1);
         const bool valid = c < HL_TW;
         const int d = r * HL_TW + c;                              // dense row inside the [8][14] store box
         const bool leader = (warp == 4 && lane == 0);
@@ -303,21 +313,22 @@ bool conv_halo_applicable(const ConvParams& p, const ConvWeights& w) {
     static int all = -1;
     if (all < 0) { const char* e = getenv("SPECB200_HALO_ALL"); all = (e && e[0] == '1') ? 1 : 0; }
     const bool shape_ok = p.kh == 3 && p.kw == 3 && p.stride == 1 && p.pad == 1 && (p.Cin % 64) == 0 && p.Cin <= 256 &&
-                          (p.Cout == 64 || p.Cout == 128 || p.Cout == 256) && w.block_n == p.Cout && p.W >= HL_TW &&
+                          (p.Cout == 64 || p.Cout == 128 || p.Cout == 256) && w.block_n == p.Cout && p.W >= 14 &&
                           (p.out_coff % 8) == 0;
     return !off && shape_ok && (all || (p.Cin == 64 && p.Cout == 64));
 }
 
-template <typename T, int BLOCK_N, int PA, int PB, bool RES>
+template <typename T, int BLOCK_N, int PA, int PB, bool RES, int G>
 static bool halo_launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s) {
-    using L = HaloSmem<BLOCK_N, PA, PB>;
+    using L = HaloSmem<BLOCK_N, PA, PB, G>;
+    constexpr int HL_TH = HaloDims<G>::TH, HL_TW = HaloDims<G>::TW, HL_PW = HaloDims<G>::PW;
     HaloMaps maps;
     maps.b = w.tmap_b;
     if (!make_tmap_nhwc(&maps.a, p.in, p.Cin, p.W, p.H, p.N, HL_PW, HL_TH + 2)) return false;
     if (!make_tmap_nhwc(&maps.out, p.out, p.out_ld, p.Wo, p.Ho, p.N, HL_TW, HL_TH)) return false;
     maps.res = maps.out;
     if (p.res != nullptr && !make_tmap_nhwc(&maps.res, p.res, p.res_ld, p.Wo, p.Ho, p.N, HL_TW, HL_TH)) return false;
-    auto kern = conv3x3_halo_kernel<T, BLOCK_N, PA, PB, RES>;
+    auto kern = conv3x3_halo_kernel<T, BLOCK_N, PA, PB, RES, G>;
     static bool attr = false;
     if (!attr) {
         if (!check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "halo smem attr")) return false;
@@ -337,12 +348,18 @@ static bool halo_launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStrea
     return check_cuda(cudaGetLastError(), "conv_halo launch");
 }
 
+static double halo_tile_eff(int H, int W, int th, int tw) {
+    return (static_cast<double>(W) / (tw * ((W + tw - 1) / tw))) * (static_cast<double>(H) / (th * ((H + th - 1) / th))) * tw / (tw + 2.0);
+}
+
 template <typename T>
 static bool halo_launch_dt(const ConvParams& p, const ConvWeights& w, cudaStream_t s) {
-    if (p.Cout == 64 && p.Cin == 64) return halo_launch_cfg<T, 64, 4, 9, true>(p, w, s);
-    if (p.Cout == 64) return halo_launch_cfg<T, 64, 4, 8, false>(p, w, s);
-    if (p.Cout == 128) return halo_launch_cfg<T, 128, 3, 5, false>(p, w, s);
-    return halo_launch_cfg<T, 256, 2, 3, false>(p, w, s);
+    const bool wide = halo_tile_eff(p.Ho, p.Wo, 4, 30) > halo_tile_eff(p.Ho, p.Wo, 8, 14);     // fraction of GEMM rows that are real outputs
+    if (p.Cout == 64 && p.Cin == 64)
+        return wide ? halo_launch_cfg<T, 64, 4, 9, true, 1>(p, w, s) : halo_launch_cfg<T, 64, 4, 9, true, 0>(p, w, s);
+    if (p.Cout == 64) return halo_launch_cfg<T, 64, 4, 8, false, 0>(p, w, s);
+    if (p.Cout == 128) return halo_launch_cfg<T, 128, 3, 5, false, 0>(p, w, s);
+    return halo_launch_cfg<T, 256, 2, 3, false, 0>(p, w, s);
 }
 
 bool conv_halo_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s) {
