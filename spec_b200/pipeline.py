@@ -103,6 +103,41 @@ def all_gather_records(record, group=None):
     return out
 
 
+class RecordGatherer:
+    """Overlapped form of ``all_gather_records`` for a steady-state loop: the gather of step i runs on NCCL's stream
+    while step i+1 computes.  Two send/receive buffer pairs alternate; ``submit`` returns the gathered buffer of the
+    PREVIOUS step (None on the first call), ``flush`` the last one."""
+
+    def __init__(self, batch_local, device, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        world = dist.get_world_size(group)
+        self.send = [torch.empty(batch_local, RECORD_FLOATS, dtype=torch.float32, device=device) for _ in range(2)]
+        self.recv = [torch.empty(world * batch_local, RECORD_FLOATS, dtype=torch.float32, device=device) for _ in range(2)]
+        self.work = [None, None]
+        self.i = 0
+
+    def submit(self, record):
+        k = self.i & 1
+        if self.work[k] is not None:          # buffers k were used two steps ago
+            self.work[k].wait()
+        self.send[k].copy_(record, non_blocking=True)             # the graph's record buffer is overwritten by the next replay
+        self.work[k] = self.dist.all_gather_into_tensor(self.recv[k], self.send[k], group=self.group, async_op=True)
+        prev = None
+        if self.i > 0:
+            self.work[k ^ 1].wait()
+            prev = self.recv[k ^ 1]
+        self.i += 1
+        return prev
+
+    def flush(self):
+        if self.i == 0:
+            return None
+        k = (self.i - 1) & 1
+        self.work[k].wait()
+        return self.recv[k]
+
+
 def shard_range(total, rank, world):
     """Contiguous batch split: rank r owns images [lo, hi)."""
     per = (total + world - 1) // world

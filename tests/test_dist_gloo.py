@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from spec_b200.pipeline import shard_range, all_gather_records, unpack_record, RECORD_FLOATS
+from spec_b200.pipeline import shard_range, all_gather_records, unpack_record, RecordGatherer, RECORD_FLOATS
 
 
 def test_shard_range_covers_batch():
@@ -43,6 +43,15 @@ def _worker(rank, world, port, total, q):
     d = unpack_record(full)
     ok = ok and d['smpl_vertices'].shape == (total, 6890, 3) and d['cam_angles'].shape == (total, 3)
     ok = ok and float(d['pred_cam_t'][total - 1, 0]) == float(exp[total - 1, 20670 + 147 + 98])
+    # overlapped form used by the steady-state loop: results come back one step late, in order
+    g = RecordGatherer(hi - lo, torch.device('cpu'))
+    outs = []
+    for step in range(3):
+        prev = g.submit(rec + step)
+        if prev is not None:
+            outs.append(prev.clone())
+    outs.append(g.flush().clone())
+    ok = ok and len(outs) == 3 and all(torch.equal(o, exp + i) for i, o in enumerate(outs))
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, bool(ok)))
