@@ -62,3 +62,46 @@ def convert_preds_to_angles(pred_vfov, pred_pitch, pred_roll, loss_type='softarg
     if return_type == 'np':
         return tuple(o.cpu().numpy() for o in out)
     return out
+
+
+# ---- CamCalib <-> SPEC wire format: the reference hands camera parameters from camcalib_demo.py to
+# spec_demo.py through one pickle per image; the fused in-process path does not need it but can still produce it.
+def save_camcalib_pkl(output_path, image_names, angles, f_pix):
+    """Writes ``<output_path>/camcalib/<basename>.pkl`` = {'vfov','f_pix','pitch','roll'} exactly as
+    /root/reference/scripts/camcalib_demo.py:135-140,174 does (numpy scalars), from the tensors returned by
+    ``CameraRegressorNetwork.predict_camera``."""
+    import os
+    import joblib
+    import numpy as np
+    os.makedirs(os.path.join(output_path, 'camcalib'), exist_ok=True)
+    a = angles.detach().float().cpu().numpy()
+    f = f_pix.detach().float().cpu().numpy()
+    out = []
+    for i, name in enumerate(image_names):
+        p = os.path.join(output_path, 'camcalib', os.path.basename(name) + '.pkl')
+        joblib.dump({'vfov': np.float32(a[i, 0]), 'f_pix': np.float32(f[i]), 'pitch': np.float32(a[i, 1]),
+                     'roll': np.float32(a[i, 2])}, p)
+        out.append(p)
+    return out
+
+
+def load_camcalib_pkl(output_path, img_fname, orig_shape):
+    """Host mirror of /root/reference/spec/utils/cam_params.py:24-50 (``read_cam_params``) for files written above:
+    returns (cam_rotmat, cam_int, vfov, pitch, roll, focal_length) as CPU tensors / floats.  The rotation is built with
+    the same quaternion formula as the device kernel (tail.cu::euler_to_rotmat)."""
+    import math
+    import os
+    import joblib
+    d = joblib.load(os.path.join(output_path, 'camcalib', os.path.basename(img_fname) + '.pkl'))
+    pitch, roll, vfov, f = float(d['pitch']), float(d['roll']), float(d['vfov']), float(d['f_pix'])
+    hx, hz = pitch * 0.5, roll * 0.5
+    qw, qx, qy, qz = math.cos(hx) * math.cos(hz), math.sin(hx) * math.cos(hz), -math.sin(hx) * math.sin(hz), math.cos(hx) * math.sin(hz)
+    n = math.sqrt(qw * qw + qx * qx + qy * qy + qz * qz)
+    qw, qx, qy, qz = qw / n, qx / n, qy / n, qz / n
+    R = torch.tensor([[qw * qw + qx * qx - qy * qy - qz * qz, 2 * qx * qy - 2 * qw * qz, 2 * qw * qy + 2 * qx * qz],
+                      [2 * qw * qz + 2 * qx * qy, qw * qw - qx * qx + qy * qy - qz * qz, 2 * qy * qz - 2 * qw * qx],
+                      [2 * qx * qz - 2 * qw * qy, 2 * qw * qx + 2 * qy * qz, qw * qw - qx * qx - qy * qy + qz * qz]], dtype=torch.float32)
+    K = torch.zeros(3, 3)
+    K[0, 0] = K[1, 1] = f
+    K[0, 2], K[1, 2] = orig_shape[1] / 2, orig_shape[0] / 2
+    return R, K, vfov, pitch, roll, f

@@ -123,3 +123,88 @@ def test_record_layout_views():
     assert sum(v[0].numel() for v in d.values()) == sb.pipeline.RECORD_FLOATS
     d['smpl_joints2d'][0, 0, 0] = -1.0                                  # writable (losses.py:191 mutates in place)
     assert float(rec[0, 20670 + 147]) == -1.0
+
+
+# --------------------------------------------------------------------------------------- op-program compiler (host logic)
+@pytest.mark.parametrize('arch,kw', [('resnet50', {}), ('resnet34', {}), ('hrnet_w32', {'use_conv': True}),
+                                     ('hrnet_w32', {'use_conv': False}), ('hrnet_w48', {'use_conv': True})])
+def test_program_buffer_liveness(arch, kw):
+    """The compiled op program reuses activation buffers; replay it symbolically and check that no op reads a buffer
+    whose value has been overwritten since the reader's producer wrote it, that residual/src never alias dst for convs,
+    and that channel widths line up."""
+    from spec_b200.backbone import Trunk
+    from spec_b200._lib import OP_CONV, OP_MAXPOOL, OP_UPADD, OP_BILINEAR, OP_COPY
+    t = Trunk(arch, **kw)
+    P = t._program
+    version = {0: 0}                       # buffer -> version counter
+    expect = {}                            # buffer -> version its consumers were promised
+    ch = list(P.buf_ch)
+    ch[0] = 4
+    for i, o in enumerate(P.ops):
+        srcs = [o['src']] + ([o['src2']] if o['src2'] >= 0 else [])
+        for b in srcs:
+            assert b in version, f'op {i} reads undefined buffer {b}'
+        if o['type'] == OP_CONV:
+            assert o['dst'] not in srcs, f'op {i}: conv writes a buffer it reads'
+            assert (4 if o['src'] == 0 else o['cin']) == ch[o['src']]
+            assert o['dst_coff'] + o['cout'] <= ch[o['dst']]
+            if o['src2'] >= 0:
+                assert ch[o['src2']] == o['cout']
+        if o['type'] in (OP_UPADD,):
+            assert o['dst'] in version and ch[o['src']] == ch[o['dst']]
+        if o['type'] == OP_CONV and o['dst_coff'] == 0 and o['cout'] == ch[o['dst']] or o['type'] in (OP_MAXPOOL,):
+            version[o['dst']] = version.get(o['dst'], 0) + 1
+        else:
+            version.setdefault(o['dst'], 0)
+    assert t._out_buf in version
+    # every conv has exactly one weight slot and parameters under the reference's names
+    slots = [o['wslot'] for o in P.ops if o['type'] == OP_CONV]
+    assert sorted(slots) == list(range(len(P.convs)))
+    names = dict(t.named_modules())
+    for conv_path, bn_path, cout, cin, k in P.convs:
+        assert tuple(names[conv_path].weight.shape) == (cout, cin, k, k)
+        assert names[bn_path].running_var.shape == (cout,)
+
+
+def test_program_matches_oracle_op_counts():
+    """conv counts of the compiled programs equal the oracle modules' (53 / 311 / 305 convs)."""
+    import torch.nn as nn
+    from oracle import resnet as orn, hrnet as ohr
+    from spec_b200.backbone import Trunk
+    for arch, ref in (('resnet50', orn.resnet50()), ('hrnet_w32', ohr.hrnet_w32(use_conv=True))):
+        n_ref = sum(isinstance(m, nn.Conv2d) for m in ref.modules())
+        assert len(Trunk(arch)._program.convs) == n_ref
+    assert len(Trunk('hrnet_w32', use_conv=False)._program.convs) == 305
+
+
+def test_camcalib_wire_format_roundtrip(tmp_path):
+    """The CamCalib -> SPEC hand-off file (scripts/camcalib_demo.py:135-140,174; README.md:97-104) can still be written
+    and read back by read_cam_params-style code when the fused in-process path is used."""
+    import joblib
+    import numpy as np
+    from spec_b200.cam_utils import save_camcalib_pkl, load_camcalib_pkl
+    ang = torch.tensor([[0.9, 0.1, -0.05], [1.2, -0.2, 0.3]])
+    f = torch.tensor([1100.0, 700.0])
+    paths = save_camcalib_pkl(str(tmp_path), ['a.jpg', 'sub/b.png'], ang, f)
+    d = joblib.load(paths[1])
+    assert set(d) == {'vfov', 'f_pix', 'pitch', 'roll'} and abs(float(d['pitch']) + 0.2) < 1e-6
+    R, K, vfov, pitch, roll, fl = load_camcalib_pkl(str(tmp_path), 'b.png', (1080, 1920))
+    assert K[0, 2] == 960 and K[1, 2] == 540 and K[2, 2] == 0 and abs(fl - 700.0) < 1e-6
+    assert R.shape == (3, 3) and abs(float(torch.linalg.det(R)) - 1) < 1e-5
+
+
+@pytest.mark.parametrize('backbone', ['resnet50', 'resnet34', 'hrnet_w32-conv', 'hrnet_w32-interp'])
+def test_compiled_program_equals_oracle_on_cpu(backbone):
+    """Interpret the compiled op program with torch on the CPU (tests/program_interp.py) and compare with the oracle
+    trunk: validates the architecture compilation, buffer reuse, BN folding, fuse order and concat offsets -- the whole
+    host side of the trunk -- without a GPU."""
+    from tests.program_interp import run_program
+    prod, ref = make_pair(backbone, seed=9, amplify=False)
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 64, 96)
+    with torch.no_grad():
+        want = ref.backbone(x)
+    got = run_program(prod.backbone, x)
+    assert got.shape == want.shape
+    err = (got - want).abs().max().item()
+    assert err < 2e-3 * max(1.0, want.abs().max().item()), err
