@@ -329,10 +329,9 @@ static bool halo_launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStrea
     maps.res = maps.out;
     if (p.res != nullptr && !make_tmap_nhwc(&maps.res, p.res, p.res_ld, p.Wo, p.Ho, p.N, HL_TW, HL_TH)) return false;
     auto kern = conv3x3_halo_kernel<T, BLOCK_N, PA, PB, RES, G>;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.need()) {
         if (!check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "halo smem attr")) return false;
-        attr = true;
     }
     static int num_sms = 0;
     if (num_sms == 0) {

@@ -208,11 +208,10 @@ bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N,
     const long long total = static_cast<long long>(N) * tiles_h * tiles_w;
     if (total > 0x7fffffffLL) { set_error("conv_stem7: too many tiles"); return false; }
     const unsigned grid = static_cast<unsigned>(total < 2LL * num_sms ? total : 2LL * num_sms);
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.need()) {
         if (!check_cuda(cudaFuncSetAttribute(conv_stem7_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_BYTES), "stem attr")) return false;
         if (!check_cuda(cudaFuncSetAttribute(conv_stem7_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_BYTES), "stem attr")) return false;
-        attr = true;
     }
     if (prec == PREC_BF16)
         conv_stem7_kernel<__nv_bfloat16><<<grid, 256, ST_DYN_BYTES, s>>>(img, static_cast<__nv_bfloat16*>(out), w.bias, w.tmap_b, N, H, W, Ho, Wo, tiles_h, tiles_w, static_cast<int>(total));

@@ -714,11 +714,10 @@ static bool launch_pair(const ConvParams& p, ConvTcMaps maps, const ConvWeights&
     if (!make_tmap_2d(&maps.b, w.w_tc, static_cast<uint64_t>(w.cout_pad), static_cast<uint64_t>(w.K_pad), static_cast<uint64_t>(w.K_pad), BLOCK_N / 2)) return false;
     auto k0 = conv_tcp2_kernel<T, BLOCK_N, STAGES, A_TILED>;
     auto k1 = conv_tcp2_kernel<T, BLOCK_N, STAGES, A_IM2COL>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (attr_done.need()) {
         if (!check_cuda(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         if (!check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
-        attr_done = true;
     }
     if (g_num_sms == 0) {
         int dev = 0;
@@ -739,11 +738,10 @@ static bool launch_persistent(const ConvParams& p, const ConvTcMaps& maps, int m
     using L = ConvTcpSmem<BLOCK_N, STAGES>;
     auto k0 = conv_tcp_kernel<T, BLOCK_N, STAGES, A_TILED>;
     auto k1 = conv_tcp_kernel<T, BLOCK_N, STAGES, A_IM2COL>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (attr_done.need()) {
         if (!check_cuda(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         if (!check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
-        attr_done = true;
     }
     if (g_num_sms == 0) {
         int dev = 0;
@@ -798,13 +796,12 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
     auto k1 = conv_tc_kernel<T, BLOCK_N, STAGES, A_IM2COL>;
     auto k2 = conv_tc_kernel<T, BLOCK_N, STAGES, A_GATHER>;
     auto k3 = conv_tc_kernel<T, BLOCK_N, STAGES, A_STEM>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (attr_done.need()) {
         if (!check_cuda(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         if (!check_cuda(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         if (!check_cuda(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
         if (!check_cuda(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
-        attr_done = true;
     }
     const long long grid = static_cast<long long>(m_tiles) * n_tiles;
     if (grid > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return false; }

@@ -39,6 +39,19 @@ struct ConvWeights {
 };
 
 void set_error(const std::string& msg);
+
+// cudaFuncSetAttribute is per DEVICE: remember per (function instantiation, device) whether the opt-in was done.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
 bool check_cuda(cudaError_t e, const char* what);
 
 // tcgen05 implicit-GEMM conv (conv_tc.cu).  prec is PREC_BF16 or PREC_F16.

@@ -396,11 +396,10 @@ smpl_verts_kernel(const float* __restrict__ Vt, const float* __restrict__ Sd, co
 bool smpl_verts_launch(const float* Vt, const float* Sd, const float* Pd, const float* Wl, const float* Jx, const float* X,
                        int ldx, int C, const float* pf, const float* Amat, float* o_verts, long long ld_verts,
                        float* partials, int B, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.need()) {
         if (!check_cuda(cudaFuncSetAttribute(smpl_verts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(SvSmem))), "smpl_verts attr")) return false;
-        attr = true;
     }
     dim3 grid(SMPL_NVT, (B + SV_TB - 1) / SV_TB);
     smpl_verts_kernel<<<grid, 256, sizeof(SvSmem), s>>>(Vt, Sd, Pd, Wl, Jx, X, ldx, C, pf, Amat, o_verts, ld_verts, partials, B);
