@@ -147,6 +147,9 @@ class HMR(nn.Module):
         self._dirty = True
         self._device = None
         self._ws = None
+        self._graphs = {}
+        self._module_graph = os.environ.get('SPECB200_MODULE_GRAPH', '1') != '0'
+        self.graph_max_batch = 32
         self.register_load_state_dict_post_hook(lambda m, k: m._mark_dirty())
         if pretrained is not None:
             self.load_pretrained(pretrained)
@@ -237,7 +240,60 @@ class HMR(nn.Module):
     def forward(self, images, cam_rotmat=None, cam_intrinsics=None, bbox_scale=None, bbox_center=None,
                 img_w=None, img_h=None, _out=None):
         """``_out``: optional dict name -> (tensor view, per-image stride in floats) to write the outputs
-        into caller-provided (e.g. packed all-gather) storage instead of fresh tensors."""
+        into caller-provided (e.g. packed all-gather) storage instead of fresh tensors.
+
+        Small batches (the demo loop runs one forward per image with batch = #detections, spec/tester.py:143-151) are
+        launch-bound (60 kernels of a few microseconds): for B <= ``graph_max_batch`` the forward is captured once per
+        input shape into a CUDA graph and replayed (SPECB200_MODULE_GRAPH=0 disables)."""
+        if (_out is None and self._module_graph and images.is_cuda and images.shape[0] <= self.graph_max_batch
+                and images.shape[0] > 0 and not torch.cuda.is_current_stream_capturing()):
+            return self._forward_graphed(images, cam_rotmat, cam_intrinsics, bbox_scale, bbox_center, img_w, img_h)
+        return self._forward_impl(images, cam_rotmat, cam_intrinsics, bbox_scale, bbox_center, img_w, img_h, _out)
+
+    def _forward_graphed(self, images, cam_rotmat, cam_intrinsics, bbox_scale, bbox_center, img_w, img_h):
+        _lib.require_device(images)
+        dev, B = images.device, images.shape[0]
+        args = {'cam_rotmat': (cam_rotmat, (3, 3)), 'cam_intrinsics': (cam_intrinsics, (3, 3)), 'bbox_scale': (bbox_scale, ()),
+                'bbox_center': (bbox_center, (2,)), 'img_w': (img_w, ()), 'img_h': (img_h, ())}
+        key = (dev, tuple(images.shape), self.backbone.precision, tuple(k for k, (v, _) in args.items() if v is not None))
+        if self._dirty or self.backbone._dirty:
+            self._graphs.clear()                                   # weights changed: captured graphs hold stale handles
+        g = self._graphs.get(key)
+        if g is None:
+            st = {'images': torch.empty(images.shape, dtype=torch.float32, device=dev)}
+            for k, (v, shp) in args.items():
+                st[k] = None if v is None else torch.empty((B,) + shp, dtype=torch.float32, device=dev)
+            def load():
+                st['images'].copy_(images)
+                for k, (v, shp) in args.items():
+                    if v is not None:
+                        st[k].copy_(self._f32(v, B, dev, shp))
+            load()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                          # warm-up outside capture: packs weights, sizes workspaces
+                self._forward_impl(st['images'], st['cam_rotmat'], st['cam_intrinsics'], st['bbox_scale'], st['bbox_center'],
+                                   st['img_w'], st['img_h'], None)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self._forward_impl(st['images'], st['cam_rotmat'], st['cam_intrinsics'], st['bbox_scale'],
+                                          st['bbox_center'], st['img_w'], st['img_h'], None)
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            # the graph baked in raw workspace pointers: keep those tensors alive for as long as the graph lives
+            keep = [self._ws] + list(self.backbone._ws.values())
+            g = self._graphs[key] = (graph, st, outs, keep)
+        graph, st, outs, _keep = g
+        st['images'].copy_(images, non_blocking=True)
+        for k, (v, shp) in args.items():
+            if v is not None:
+                st[k].copy_(self._f32(v, B, dev, shp), non_blocking=True)
+        graph.replay()
+        return {k: v.clone() for k, v in outs.items()}             # fresh tensors owned by the caller
+
+    def _forward_impl(self, images, cam_rotmat, cam_intrinsics, bbox_scale, bbox_center, img_w, img_h, _out):
         _lib.require_device(images)
         dev = images.device
         B = images.shape[0]

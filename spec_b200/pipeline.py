@@ -83,6 +83,8 @@ class SPECPipeline:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._step(st['images'], st['bbox_scale'], st['bbox_center'], st['img_w'], st['img_h'], st['record'])
+        # the graph baked in raw workspace pointers: keep those tensors alive for as long as the graph lives
+        self._keep = [self.hmr._ws, self.camcalib._ws] + list(self.hmr.backbone._ws.values()) + list(self.camcalib.backbone._ws.values())
         self._graph, self._static = g, st
 
     def __call__(self, images, bbox_scale, bbox_center, img_w, img_h):

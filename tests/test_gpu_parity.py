@@ -473,3 +473,41 @@ def test_eval_metrics_match_oracle():
     sb.unpack_record(rec)['smpl_vertices'].copy_(pred_v.to(DEV))
     got2 = m(sb.unpack_record(rec)['smpl_vertices'], gt_keypoints_3d=gt_kp.to(DEV))
     assert torch.equal(got2['mpjpe'], m(pred_v.to(DEV), gt_keypoints_3d=gt_kp.to(DEV))['mpjpe'])
+
+
+def test_module_graph_cache_survives_shape_changes(models):
+    """HMR.forward replays a cached CUDA graph for small batches; interleaving other shapes (which re-allocates the
+    eager workspaces) and re-loading weights must not corrupt or stale the cached graphs."""
+    _, _, hmr, hmr_ref = models
+    hmr.backbone.set_precision('bf16')
+    hmr.to(DEV)
+    def run(B, seed):
+        b = synthetic_batch(B, seed=seed, device=DEV)
+        vfov, pitch, roll = synthetic_camera(B, seed=seed)
+        R, K, _ = og.cam_params_from_angles(vfov, pitch, roll, b['img_h'].cpu(), b['img_w'].cpu())
+        return hmr(b['images'], R.to(DEV), K.to(DEV), b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'])
+    a1 = run(2, 21)
+    _ = run(5, 22)                      # another cached shape
+    _ = run(40, 23)                     # eager path (B > graph_max_batch) re-allocates the workspaces
+    a2 = run(2, 21)
+    for k in a1:
+        assert torch.equal(a1[k], a2[k]), k
+        assert a1[k].data_ptr() != a2[k].data_ptr()                    # fresh tensors per call
+    import os
+    os.environ['SPECB200_MODULE_GRAPH'] = '0'
+    try:
+        hmr._module_graph = False
+        e = run(2, 21)
+    finally:
+        hmr._module_graph = True
+        os.environ.pop('SPECB200_MODULE_GRAPH', None)
+    for k in a1:
+        assert torch.equal(a1[k], e[k]), k                             # graph replay == eager launches, bit for bit
+    sd = {k: v.clone() for k, v in hmr.state_dict().items()}
+    sd2 = dict(sd); sd2['head.decshape.bias'] = sd['head.decshape.bias'] + 0.5
+    hmr.load_state_dict(sd2)
+    c = run(2, 21)
+    assert not torch.equal(c['pred_shape'], a1['pred_shape'])           # stale graphs were dropped
+    hmr.load_state_dict(sd)
+    d = run(2, 21)
+    assert torch.equal(d['pred_shape'], a1['pred_shape'])
