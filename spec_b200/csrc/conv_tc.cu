@@ -783,9 +783,16 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
     if constexpr (BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256) {
         // k>1 convs at N<=128: two co-resident one-tile CTAs feed the tensor pipe better than one persistent CTA (measured);
         // at N=256 the operand bytes per MMA cycle drop to 96 B and the persistent kernel (overlapped epilogue) wins.
+        if (g_use_2cta < 0) { const char* e = getenv("SPECB200_NO_2CTA"); g_use_2cta = (e && e[0] == '1') ? 0 : 1; }
+        static int pair128 = -1;           // SPECB200_PAIR128=1: CTA pairs also for 128-wide tiles with K >= 256 (experiment)
+        if (pair128 < 0) { const char* e = getenv("SPECB200_PAIR128"); pair128 = (e && e[0] == '1') ? 1 : 0; }
+        const bool tma_fed = (mode == A_TILED || mode == A_IM2COL) && (p.Cout & 63) == 0 && p.Cout <= 2048;
+        if constexpr (BLOCK_N == 128) {
+            if (!g_no_persist && tma_fed && g_use_2cta && pair128 && m_tiles >= 2 && p.K >= 256)
+                return launch_pair<T, 128, 6>(p, maps, w, mode, m_tiles, n_tiles, s);
+        }
         const bool one_tile_better = p.kh * p.kw > 1 && BLOCK_N < 256;
-        if (!g_no_persist && !one_tile_better && (mode == A_TILED || mode == A_IM2COL) && (p.Cout & 63) == 0 && p.Cout <= 2048) {
-            if (g_use_2cta < 0) { const char* e = getenv("SPECB200_NO_2CTA"); g_use_2cta = (e && e[0] == '1') ? 0 : 1; }
+        if (!g_no_persist && !one_tile_better && tma_fed) {
             if constexpr (BLOCK_N == 256) {
                 if (g_use_2cta && m_tiles >= 2) return launch_pair<T, 256, 4>(p, maps, w, mode, m_tiles, n_tiles, s);
             }
