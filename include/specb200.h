@@ -177,6 +177,37 @@ int specb200_eval_forward(specb200_eval_t* t, int32_t batch, const float* pred_v
                           float* pred_keypoints14_dev, void* stream);
 void specb200_eval_destroy(specb200_eval_t* t);
 
+/* ---- input side on the device: uint8 frame -> network inputs, BIT-EXACT with the
+ *      libraries the reference calls (cv2.warpAffine 8-bit fixed-point path; Pillow ImagingResample 8-bit path;
+ *      torchvision ToTensor + Normalize in float32) ------------------------------------------------------------- */
+typedef struct specb200_preproc specb200_preproc_t;
+/* mean3/std3: host float[3] (spec/constants.py:20-21).  Builds the 3x256 float32 ToTensor+Normalize table. */
+int specb200_preproc_create(specb200_preproc_t** out, const float* mean3, const float* std3);
+/* Person crops = get_single_image_crop_demo(img, bbox, kp_2d=None, scale, crop_size) of pare.utils.vibe_image_utils as
+ * called at /root/reference/spec/tester.py:118-125 (gen_trans_from_patch_cv -> cv2.getAffineTransform ->
+ * cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) -> ToTensor -> Normalize), all n detections of a frame in one launch
+ * per 32 boxes.  image_dev: uint8 [height][width][3] with row pitch row_stride_bytes (bgr != 0: channels are B,G,R as
+ * cv2.imread returns them and are swapped like the cv2.cvtColor(BGR2RGB) of tester.py:105).  boxes_host: HOST
+ * double [n][4] = (c_x, c_y, w, h) in pixels.  out_dev: float32 [n][3][crop][crop]; raw_dev: uint8 [n][crop][crop][3]
+ * RGB (the "raw_img" return value) or NULL. */
+int specb200_preproc_crop(specb200_preproc_t* t, const uint8_t* image_dev, int32_t height, int32_t width,
+                          int64_t row_stride_bytes, int32_t bgr, const double* boxes_host, int32_t n, double scale,
+                          int32_t crop_size, float* out_dev, uint8_t* raw_dev, void* stream);
+/* Host only: the forward 2x3 matrices ("trans", what kp_2d is mapped with) and/or the dst->src matrices of the boxes;
+ * either output may be NULL.  [n][6] row-major doubles. */
+int specb200_preproc_crop_transforms(const double* boxes_host, int32_t n, double scale, int32_t crop_size,
+                                     double* trans_host, double* inv_host);
+/* CamCalib input = transforms.Compose([Resize(min_size), ToTensor(), Normalize(...)]) on a PIL image,
+ * /root/reference/camcalib/pano_dataset.py:156-162.  resized_shape is torchvision's rule (short side -> min_size). */
+int specb200_preproc_resized_shape(int32_t height, int32_t width, int32_t min_size, int32_t* out_h, int32_t* out_w);
+int64_t specb200_preproc_resize_workspace_bytes(int32_t height, int32_t width, int32_t out_h, int32_t out_w);
+/* out_dev: float32 [3][out_h][out_w]; raw_dev: uint8 [out_h][out_w][3] RGB or NULL.  The first call for a new
+ * (size -> size) pair uploads its coefficient table with a blocking copy (do it outside stream capture). */
+int specb200_preproc_resize(specb200_preproc_t* t, const uint8_t* image_dev, int32_t height, int32_t width,
+                            int64_t row_stride_bytes, int32_t bgr, int32_t out_h, int32_t out_w, void* workspace_dev,
+                            int64_t workspace_bytes, float* out_dev, uint8_t* raw_dev, void* stream);
+void specb200_preproc_destroy(specb200_preproc_t* t);
+
 /* ---- standalone ops (unit tests / building blocks) -------------------------------------------- */
 /* out[m][n] = sum_k a[m][k] w[n][k] + bias[n] ; fp32 */
 int specb200_linear_f32(const float* a_dev, int32_t lda, const float* w_dev, int32_t ldw, const float* bias_dev,

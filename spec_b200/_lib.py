@@ -83,6 +83,15 @@ _PROTOS = {
     'specb200_eval_forward': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'specb200_eval_destroy': (None, [C.c_void_p]),
+    'specb200_preproc_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    'specb200_preproc_crop': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'specb200_preproc_crop_transforms': (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
+    'specb200_preproc_resized_shape': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'specb200_preproc_resize_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    'specb200_preproc_resize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'specb200_preproc_destroy': (None, [C.c_void_p]),
     'specb200_linear_f32': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }

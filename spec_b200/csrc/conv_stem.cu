@@ -14,6 +14,7 @@
 // The CTA is sequential per tile; two to three co-resident CTAs per SM (93 KB smem each) overlap the phases.
 #include "common.cuh"
 #include "internal.h"
+#include <stdlib.h>
 
 namespace sb {
 
@@ -195,6 +196,203 @@ conv_stem7_kernel(const float* __restrict__ img, T* __restrict__ out, const floa
     }
 }
 
+// ------------------------------------------------------------------------------------------ pipelined version
+// Same arithmetic, warp-specialised and double-buffered so that the phases of consecutive tiles overlap inside ONE
+// persistent CTA per SM (the first version ran them back to back in two co-resident CTAs and sat at 3.4x its floor,
+// profiles/README.md):
+//   warps 4-11 (builders): input patch -> smem (double-buffered), A rows of tile i into A[i & 1]
+//   warp  12   (MMA)     : 11 x tcgen05.mma (the 12th K-step is all padding and is skipped) into TMEM[i & 1]
+//   warps 0-3  (epilogue): TMEM -> +bias -> ReLU -> 16 bit -> swizzled staging[i & 1] -> ONE 4-D TMA store (clips edges)
+// so the per-tile cost is max(build, MMA ~ 960 cycles, epilogue) instead of their sum.
+constexpr int STP_THREADS = 416;
+constexpr int STP_OFF_A = 0;                                   // 2 x 49152
+constexpr int STP_OFF_B = 2 * ST_A_BYTES;                      // 24576
+constexpr int STP_OFF_STAGE = STP_OFF_B + ST_B_BYTES;          // 2 x 16384
+constexpr int STP_OFF_PATCH = STP_OFF_STAGE + 2 * ST_STAGE_BYTES;   // 2 x 6144
+constexpr int STP_OFF_BIAS = STP_OFF_PATCH + 2 * 6144;
+constexpr int STP_OFF_BAR = STP_OFF_BIAS + 256;                // b, a_full[2], a_empty[2], t_full[2], t_empty[2], tmem ptr
+constexpr int STP_DYN_BYTES = STP_OFF_BAR + 128 + 1024;
+static_assert(STP_DYN_BYTES <= 232448, "stem: shared memory");
+
+template <typename T>
+__global__ void __launch_bounds__(STP_THREADS, 1)
+conv_stem7p_kernel(const float* __restrict__ img, const float* __restrict__ bias, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_out, int N, int H, int W, int tiles_h, int tiles_w, int total_tiles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t a_base = sbase + STP_OFF_A;
+    const uint32_t b_base = sbase + STP_OFF_B;
+    const uint32_t st_base = sbase + STP_OFF_STAGE;
+    T* patch0 = reinterpret_cast<T*>(sgen + STP_OFF_PATCH);
+    float* sbias = reinterpret_cast<float*>(sgen + STP_OFF_BIAS);
+    const uint32_t bar_b = sbase + STP_OFF_BAR;
+    const uint32_t bar_afull = bar_b + 8, bar_aempty = bar_b + 24, bar_tfull = bar_b + 40, bar_tempty = bar_b + 56;
+    volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sgen + STP_OFF_BAR + 72);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_afull + i * 8, 8);                    // one arrival per builder warp
+            mbar_init(bar_aempty + i * 8, 1);                   // tcgen05.commit
+            mbar_init(bar_tfull + i * 8, 1);                    // tcgen05.commit
+            mbar_init(bar_tempty + i * 8, 4);                   // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (tid < 64) sbias[tid] = bias[tid];
+    for (int i = tid; i < 2 * (6144 / 2); i += STP_THREADS) patch0[i] = DT<T>::from_f(0.f);          // both patch buffers: pad columns stay zero
+    if (warp == 12) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), 128);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp >= 4 && warp < 12) {
+        // ================= builders
+        const int wb = warp - 4, bt = tid - 128;
+        const size_t plane = static_cast<size_t>(H) * W;
+        float pre[16];
+        auto prefetch = [&](int tile) {
+            const int tw = tile % tiles_w;
+            const int th = (tile / tiles_w) % tiles_h;
+            const int n = tile / (tiles_w * tiles_h);
+            const int ih0 = 2 * th * ST_TH - 3, iw0 = 2 * tw * ST_TW - 3;
+            const float* src = img + static_cast<size_t>(n) * 3 * plane;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int row = wb + 8 * k;
+                const int c = row >= 42 ? 2 : (row >= 21 ? 1 : 0);
+                const int r = row - c * 21;
+                const int ih = ih0 + r;
+                const bool rok = row < 63 && static_cast<unsigned>(ih) < static_cast<unsigned>(H);
+                const float* rp = src + c * plane + static_cast<size_t>(rok ? ih : 0) * W;
+                const int iwa = iw0 + lane, iwb = iw0 + lane + 32;
+                pre[2 * k] = (rok && static_cast<unsigned>(iwa) < static_cast<unsigned>(W)) ? __ldg(rp + iwa) : 0.f;
+                pre[2 * k + 1] = (rok && lane < ST_PC - 32 && static_cast<unsigned>(iwb) < static_cast<unsigned>(W)) ? __ldg(rp + iwb) : 0.f;
+            }
+        };
+        if (static_cast<int>(blockIdx.x) < total_tiles) prefetch(blockIdx.x);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            T* patch = patch0 + s * (6144 / 2);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int row = wb + 8 * k;
+                if (row < 63) {
+                    patch[row * ST_PP + lane] = DT<T>::from_f(pre[2 * k]);
+                    if (lane < ST_PC - 32) patch[row * ST_PP + lane + 32] = DT<T>::from_f(pre[2 * k + 1]);
+                }
+            }
+            named_bar_sync(2, 256);                             // patch[s] complete; also orders the reuse of patch[s ^ 1]
+            if (tile + static_cast<int>(gridDim.x) < total_tiles) prefetch(tile + gridDim.x);
+            mbar_wait(bar_aempty + s * 8, ph ^ 1);              // the MMAs of tile it-2 have consumed A[s]
+            {
+                const int t = bt & 127, half = bt >> 7;
+                const int lr = t >> 4, lc = t & 15;
+                const uint32_t sw = static_cast<uint32_t>(t) & 7u;
+                const uint32_t a_s = a_base + s * ST_A_BYTES;
+#pragma unroll
+                for (int jj = 0; jj < 11; ++jj) {
+                    const int j = half * 11 + jj;               // 21 real chunks + one zero chunk (second half of K-step 11)
+                    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                    if (j < 21) {
+                        const int c = j / 7, kh = j - c * 7;
+                        const uint32_t* sp = reinterpret_cast<const uint32_t*>(patch + (c * ST_PR + 2 * lr + kh) * ST_PP + 2 * lc);
+                        w0 = sp[0]; w1 = sp[1]; w2 = sp[2]; w3 = sp[3];
+                    }
+                    const uint32_t dst = a_s + (j >> 3) * 16384 + static_cast<uint32_t>(t) * 128u + (((j & 7) ^ sw) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afull + s * 8);
+        }
+    } else if (warp == 12) {
+        // ================= MMA issuer
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_b);
+            mbar_arrive_expect_tx(bar_b, ST_B_BYTES);            // weights: resident for the whole kernel
+            for (int kb = 0; kb < ST_KB; ++kb) tma_load_2d(b_base + kb * 8192, &tmap_b, bar_b, kb * 64, 0);
+            mbar_wait(bar_b, 0);
+            constexpr uint32_t idesc = umma_idesc_f16(DT<T>::umma_fmt, 128, 64);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(bar_tempty + s * 8, ph ^ 1);          // epilogue drained accumulator s
+                mbar_wait(bar_afull + s * 8, ph);
+                tc_fence_after();
+                const uint32_t a_s = a_base + s * ST_A_BYTES;
+                const uint32_t acc = tmem_base + s * 64;
+#pragma unroll
+                for (int ks = 0; ks < 11; ++ks)
+                    umma_f16(acc, umma_desc_sw128(a_s + (ks >> 2) * 16384 + (ks & 3) * 32),
+                             umma_desc_sw128(b_base + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, static_cast<uint32_t>(ks != 0));
+                umma_commit(bar_aempty + s * 8);
+                umma_commit(bar_tfull + s * 8);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue (warps 0-3: TMEM lane quarter = warp)
+        const int row = warp * 32 + lane;
+        const uint32_t sw = static_cast<uint32_t>(row) & 7u;
+        const bool leader = tid == 0;
+        if (leader) tma_prefetch_desc(&tmap_out);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            const int tw = tile % tiles_w;
+            const int th = (tile / tiles_w) % tiles_h;
+            const int n = tile / (tiles_w * tiles_h);
+            mbar_wait(bar_tfull + s * 8, ph);
+            tc_fence_after();
+            uint32_t va[32], vb[32];
+            const uint32_t acc = tmem_base + s * 64 + (static_cast<uint32_t>(warp * 32) << 16);
+            tmem_ld_32x32(acc, va);
+            tmem_ld_32x32(acc + 32, vb);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + s * 8);     // accumulator s may be overwritten
+            if (leader) tma_store_wait_read<1>();               // the store of tile it-2 has finished reading staging[s]
+            named_bar_sync(3, 128);
+            const uint32_t st_s = st_base + s * ST_STAGE_BYTES + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    f[e] = fmaxf(__uint_as_float(q < 4 ? va[(q & 3) * 8 + e] : vb[(q & 3) * 8 + e]) + sbias[q * 8 + e], 0.f);
+                const uint32_t o0 = DT<T>::pack2(f[0], f[1]), o1 = DT<T>::pack2(f[2], f[3]);
+                const uint32_t o2 = DT<T>::pack2(f[4], f[5]), o3 = DT<T>::pack2(f[6], f[7]);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + ((static_cast<uint32_t>(q) ^ sw) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
+            if (leader) {
+                tma_store_4d(&tmap_out, st_base + s * ST_STAGE_BYTES, 0, tw * ST_TW, th * ST_TH, n);
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_read0();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
 bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N, int H, int W, int Ho, int Wo, int prec,
                        cudaStream_t s) {
     if (!w.has_tmap || !w.stem7) { set_error("conv_stem7: weights not packed for the stem kernel"); return false; }
@@ -207,6 +405,24 @@ bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N,
     const int tiles_h = (Ho + ST_TH - 1) / ST_TH, tiles_w = (Wo + ST_TW - 1) / ST_TW;
     const long long total = static_cast<long long>(N) * tiles_h * tiles_w;
     if (total > 0x7fffffffLL) { set_error("conv_stem7: too many tiles"); return false; }
+    static int v1 = -1;                                          // SPECB200_STEM_V1=1: the first (non-pipelined) kernel, for A/B runs
+    if (v1 < 0) { const char* e = getenv("SPECB200_STEM_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
+    if (!v1) {
+        CUtensorMap tmap_out;
+        if (!make_tmap_nhwc(&tmap_out, out, 64, Wo, Ho, N, ST_TW, ST_TH)) return false;
+        static DeviceOnce attr_p;
+        if (attr_p.need()) {
+            if (!check_cuda(cudaFuncSetAttribute(conv_stem7p_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STP_DYN_BYTES), "stem attr")) return false;
+            if (!check_cuda(cudaFuncSetAttribute(conv_stem7p_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, STP_DYN_BYTES), "stem attr")) return false;
+        }
+        const unsigned gridp = static_cast<unsigned>(total < num_sms ? total : num_sms);
+        if (prec == PREC_BF16)
+            conv_stem7p_kernel<__nv_bfloat16><<<gridp, STP_THREADS, STP_DYN_BYTES, s>>>(img, w.bias, w.tmap_b, tmap_out, N, H, W, tiles_h, tiles_w, static_cast<int>(total));
+        else if (prec == PREC_F16)
+            conv_stem7p_kernel<__half><<<gridp, STP_THREADS, STP_DYN_BYTES, s>>>(img, w.bias, w.tmap_b, tmap_out, N, H, W, tiles_h, tiles_w, static_cast<int>(total));
+        else { set_error("conv_stem7: 16-bit precisions only"); return false; }
+        return check_cuda(cudaGetLastError(), "conv_stem7p launch");
+    }
     const unsigned grid = static_cast<unsigned>(total < 2LL * num_sms ? total : 2LL * num_sms);
     static DeviceOnce attr;
     if (attr.need()) {

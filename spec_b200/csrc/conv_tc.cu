@@ -388,16 +388,23 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
 // short-K layers are bound by the epilogue's conversion work, so it gets 8 warps).
 constexpr int CONV_TCP_THREADS = 384;          // warps 0-3: TMA / MMA / TMEM / idle; warps 4-11: epilogue (2 column halves)
 
-template <int BLOCK_N, int STAGES>
+// Epilogue staging: NBUF buffers of TILE_M x EPI_N 16-bit values (one 128B-swizzled TMA box each).  Life cycle of a
+// buffer: [residual TMA load ->] combine in place -> TMA store.  With four 64-column buffers the residual of item i+2 is
+// requested at the top of item i into the buffer whose store was issued at the end of item i-2 (long drained), so the
+// leader never waits for a store and 32 KB of residual per SM are in flight ahead of the combine; the first version
+// (two 128-column buffers, same 64 KB) stalled for the previous item's store at the top of EVERY item and had at most
+// one residual tile in flight (ncu: 'barrier' was the top stall of the 1x1 convs, profiles/ncu_r01c.md).
+template <int BLOCK_N, int STAGES, int NBUF = 4>
 struct ConvTcpSmem {
     static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
-    static constexpr int EPI_N = BLOCK_N < 128 ? BLOCK_N : 128;       // epilogue sub-tile width (columns)
+    static constexpr int EPI_N = 64;                                  // epilogue sub-tile width (columns)
+    static constexpr int EPI_BUFS = NBUF;
     static constexpr int EPI_BYTES = TILE_M * EPI_N * 2;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
     static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-    static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BYTES;        // full[S], empty[S], tfull[2], tempty[2], rfull[2]
-    static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 6) * 8;
+    static constexpr int BAR_OFF = EPI_OFF + NBUF * EPI_BYTES;     // full[S], empty[S], tfull[2], tempty[2], rfull[NBUF]
+    static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4 + NBUF) * 8;
     static constexpr int BIAS_OFF = (TMEMPTR_OFF + 8 + 15) / 16 * 16;
     static constexpr int MAX_COUT = 2048;
     static constexpr int TOTAL = BIAS_OFF + MAX_COUT * 4;
@@ -411,6 +418,9 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
 {
     static_assert(A_MODE == A_TILED || A_MODE == A_IM2COL, "persistent kernel is TMA-fed");
     using L = ConvTcpSmem<BLOCK_N, STAGES>;
+    constexpr int NBUF = L::EPI_BUFS;
+    constexpr int RES_AHEAD = NBUF > 2 ? NBUF - 2 : 1;            // residual prefetch distance in epilogue items
+    constexpr int ST_PENDING = NBUF - RES_AHEAD - 1;              // bulk-store groups that may still be reading smem
     constexpr int TMEM_COLS = 2 * BLOCK_N;
     constexpr int EPI_N = L::EPI_N;
     constexpr int NSUB = BLOCK_N / EPI_N;                        // 128-column epilogue sub-tiles per accumulator
@@ -436,7 +446,8 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + a * 8, 1); mbar_init(bar_tempty + a * 8, 8); mbar_init(bar_rfull + a * 8, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + a * 8, 1); mbar_init(bar_tempty + a * 8, 8); }
+        for (int a = 0; a < NBUF; ++a) mbar_init(bar_rfull + a * 8, 1);
         mbar_fence_init();
     }
     for (int c = threadIdx.x; c < p.Cout; c += CONV_TCP_THREADS) sbias[c] = p.bias[c];
@@ -523,8 +534,12 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
         const int t = q4 * 32 + lane;
         const bool leader = (warp == 4 && lane == 0);
         const uint32_t sw = static_cast<uint32_t>(t) & 7u;
-        // epilogue work items are (tile, sub-tile h); staging buffer / residual barrier e = item & 1
-        auto issue_res = [&](int tile, int h, uint32_t e) {
+        // epilogue work items are (tile, 64-column sub-tile h); item j uses staging buffer / residual barrier j % NBUF
+        auto issue_res = [&](uint32_t j) {                          // residual of this CTA's item j
+            const int tile = static_cast<int>(blockIdx.x + (j / NSUB) * gridDim.x);
+            if (tile >= total_tiles) return;
+            const int h = static_cast<int>(j % NSUB);
+            const uint32_t e = j % NBUF;
             const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
             mbar_arrive_expect_tx(bar_rfull + e * 8, L::EPI_BYTES);
 #pragma unroll
@@ -532,7 +547,10 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
                 tma_load_2d(e_base + e * L::EPI_BYTES + bx * (TILE_M * 128), &maps.res, bar_rfull + e * 8,
                             n_tile * BLOCK_N + h * EPI_N + bx * 64, m_tile * TILE_M);
         };
-        if (leader && has_res && static_cast<int>(blockIdx.x) < total_tiles) issue_res(blockIdx.x, 0, 0);
+        // two buffers and no residual: the drain check moves to just before the barrier (see below)
+        const bool wait_at_top = has_res || NBUF > 2;
+        if (leader && has_res)
+            for (int d = 0; d < RES_AHEAD; ++d) issue_res(d);
         uint32_t tc = 0, ec = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
@@ -540,13 +558,10 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
             const int n0 = n_tile * BLOCK_N;
 #pragma unroll 1
             for (int h = 0; h < NSUB; ++h, ++ec) {
-                const uint32_t e = ec & 1, eph = (ec >> 1) & 1;
-                if (leader) {
-                    tma_store_wait_read0();                        // the previous item's store has finished reading buffer e^1
-                    if (has_res) {
-                        if (h + 1 < NSUB) issue_res(tile, h + 1, e ^ 1);
-                        else if (tile + static_cast<int>(gridDim.x) < total_tiles) issue_res(tile + gridDim.x, 0, e ^ 1);
-                    }
+                const uint32_t e = ec % NBUF, eph = (ec / NBUF) & 1;
+                if (leader && wait_at_top) {
+                    tma_store_wait_read<ST_PENDING>();             // the last store out of buffer (ec + RES_AHEAD) % NBUF has drained
+                    if (has_res) issue_res(ec + RES_AHEAD);
                 }
                 if (h == 0) {
                     mbar_wait(bar_tfull + a * 8, aph);
@@ -596,6 +611,9 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
                     if (lane == 0) mbar_arrive(bar_tempty + a * 8);    // accumulator a may be overwritten
                 }
                 fence_proxy_async_smem();
+                // two buffers, no residual: the store of the previous item (out of the buffer the NEXT item writes) had this
+                // whole item to drain; checking it here, after the leader's own share of the work, costs nothing
+                if (leader && !wait_at_top) tma_store_wait_read0();
                 named_bar_sync(1, 256);
                 if (leader) {
 #pragma unroll

@@ -10,16 +10,17 @@
 //   own 128 accumulator rows through the same double-buffered TMA-store epilogue.
 #pragma once
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int NBUF = 4>
 struct ConvTc2Smem {
     static constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * TILE_K * 2;      // half of the weight tile per CTA
-    static constexpr int EPI_N = BLOCK_N < 128 ? BLOCK_N : 128;
+    static constexpr int EPI_N = 64;                                       // see ConvTcpSmem: four 64-column staging buffers
+    static constexpr int EPI_BUFS = NBUF;
     static constexpr int EPI_BYTES = TILE_M * EPI_N * 2;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
     static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-    static constexpr int BAR_OFF = EPI_OFF + 2 * EPI_BYTES;                // full[S], empty[S], tfull[2], tempty[2], rfull[2]
-    static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 6) * 8;
+    static constexpr int BAR_OFF = EPI_OFF + NBUF * EPI_BYTES;             // full[S], empty[S], tfull[2], tempty[2], rfull[NBUF]
+    static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4 + NBUF) * 8;
     static constexpr int BIAS_OFF = (TMEMPTR_OFF + 8 + 15) / 16 * 16;
     static constexpr int MAX_COUT = 2048;
     static constexpr int TOTAL = BIAS_OFF + MAX_COUT * 4;
@@ -34,6 +35,9 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
 {
     static_assert(A_MODE == A_TILED || A_MODE == A_IM2COL, "pair kernel is TMA-fed");
     using L = ConvTc2Smem<BLOCK_N, STAGES>;
+    constexpr int NBUF = L::EPI_BUFS;
+    constexpr int RES_AHEAD = NBUF > 2 ? NBUF - 2 : 1;            // residual prefetch distance in epilogue items
+    constexpr int ST_PENDING = NBUF - RES_AHEAD - 1;              // bulk-store groups that may still be reading smem
     constexpr int TMEM_COLS = 2 * BLOCK_N;
     constexpr int EPI_N = L::EPI_N;
     constexpr int NSUB = BLOCK_N / EPI_N;
@@ -62,7 +66,8 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 2); mbar_init(bar_empty + s * 8, 1); }   // full: both producers
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + a * 8, 1); mbar_init(bar_tempty + a * 8, 16); mbar_init(bar_rfull + a * 8, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + a * 8, 1); mbar_init(bar_tempty + a * 8, 16); }
+        for (int a = 0; a < NBUF; ++a) mbar_init(bar_rfull + a * 8, 1);
         mbar_fence_init();
     }
     for (int c = threadIdx.x; c < p.Cout; c += CONV_TCP_THREADS) sbias[c] = p.bias[c];
@@ -148,7 +153,11 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
         const bool leader = (warp == 4 && lane == 0);
         const uint32_t sw = static_cast<uint32_t>(t) & 7u;
         const uint32_t lead_tempty = mapa_u32(bar_tempty, 0);
-        auto issue_res = [&](int tile, int h, uint32_t e) {
+        auto issue_res = [&](uint32_t j) {                          // residual of this CTA's epilogue item j
+            const int tile = first_tile + static_cast<int>(j / NSUB) * tile_step;
+            if (tile >= total_tiles) return;
+            const int h = static_cast<int>(j % NSUB);
+            const uint32_t e = j % NBUF;
             const int n_tile = tile % n_tiles, m_tile = (tile / n_tiles) * 2 + static_cast<int>(rank);
             mbar_arrive_expect_tx(bar_rfull + e * 8, L::EPI_BYTES);
 #pragma unroll
@@ -156,7 +165,9 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
                 tma_load_2d(e_base + e * L::EPI_BYTES + bx * (TILE_M * 128), &maps.res, bar_rfull + e * 8,
                             n_tile * BLOCK_N + h * EPI_N + bx * 64, m_tile * TILE_M);
         };
-        if (leader && has_res && first_tile < total_tiles) issue_res(first_tile, 0, 0);
+        const bool wait_at_top = has_res || NBUF > 2;
+        if (leader && has_res)
+            for (int d = 0; d < RES_AHEAD; ++d) issue_res(d);
         uint32_t tc = 0, ec = 0;
         for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tc) {
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
@@ -164,13 +175,10 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
             const int n0 = n_tile * BLOCK_N;
 #pragma unroll 1
             for (int h = 0; h < NSUB; ++h, ++ec) {
-                const uint32_t e = ec & 1, eph = (ec >> 1) & 1;
-                if (leader) {
-                    tma_store_wait_read0();
-                    if (has_res) {
-                        if (h + 1 < NSUB) issue_res(tile, h + 1, e ^ 1);
-                        else if (tile + tile_step < total_tiles) issue_res(tile + tile_step, 0, e ^ 1);
-                    }
+                const uint32_t e = ec % NBUF, eph = (ec / NBUF) & 1;
+                if (leader && wait_at_top) {
+                    tma_store_wait_read<ST_PENDING>();             // the last store out of buffer (ec + RES_AHEAD) % NBUF has drained
+                    if (has_res) issue_res(ec + RES_AHEAD);
                 }
                 if (h == 0) { mbar_wait(bar_tfull + a * 8, aph); tc_fence_after(); }
                 if (has_res) mbar_wait(bar_rfull + e * 8, eph);
@@ -217,6 +225,7 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
                     if (lane == 0) mbar_arrive_cluster(lead_tempty + a * 8);   // tell the leader's MMA thread (count 16 = 8 warps x 2 CTAs)
                 }
                 fence_proxy_async_smem();
+                if (leader && !wait_at_top) tma_store_wait_read0();
                 named_bar_sync(1, 256);
                 if (leader) {
 #pragma unroll

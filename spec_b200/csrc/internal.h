@@ -63,6 +63,9 @@ int conv_tc_pick_block_n(int cout, int K);
 bool conv_halo_applicable(const ConvParams& p, const ConvWeights& w);
 bool conv_halo_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s);
 
+// 4-D tiled TMA descriptor over an NHWC 16-bit tensor: box = 64 channels x box_w x box_h x 1, 128-byte swizzle (conv_halo.cu)
+bool make_tmap_nhwc(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int N, int box_w, int box_h);
+
 // dedicated 7x7/2 stem (conv_stem.cu): reads the fp32 NCHW image directly, writes NHWC 16-bit [N,Ho,Wo,64]
 bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N, int H, int W, int Ho, int Wo, int prec,
                        cudaStream_t s);

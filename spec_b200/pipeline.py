@@ -110,6 +110,40 @@ class SPECPipeline:
     def __call__(self, images, bbox_scale, bbox_center, img_w, img_h):
         return unpack_record(self.forward_packed(images, bbox_scale, bbox_center, img_w, img_h))
 
+    @torch.no_grad()
+    def run_on_frame(self, frame, detections, bgr=False, camcalib_min_size=600, crop_size=224, preprocessor=None):
+        """One iteration of the demo loop (/root/reference/spec/tester.py:99-167) for a frame that is already on the GPU:
+        ``frame`` uint8 (H, W, 3) [``bgr=True`` if it is what cv2.imread returns]; ``detections`` (N, 4) host array of
+        (c_x, c_y, size, size) boxes as the detector produces them (tester.py:101,116).
+
+        CamCalib sees the whole frame at min-side ``camcalib_min_size`` (camcalib/pano_dataset.py:156-162) and yields ONE
+        camera for the frame (scripts/camcalib_demo.py:112-140, f_pix from the original height); every detection is
+        cropped on the device (tester.py:118-125), ``bbox_scale = size / 200``, ``bbox_center = (c_x, c_y)``
+        (tester.py:127-128).  Returns the output dict for the N detections plus ``cam_angles`` (N, 3) and the crops
+        (``inp_images``); an empty dict when there are no detections (tester.py:102-103 skips the frame)."""
+        import numpy as np
+        from .preprocess import default_preprocessor
+        _lib.require_device(frame)
+        det = np.asarray(detections, dtype=np.float64).reshape(-1, 4)
+        n = det.shape[0]
+        if n == 0:
+            return {}
+        P = preprocessor or default_preprocessor()
+        dev = frame.device
+        H, W = int(frame.shape[0]), int(frame.shape[1])
+        full = P.resize(frame, min_size=camcalib_min_size, bgr=bgr)
+        angles, R, K, _ = self.camcalib.predict_camera(full, H, W)
+        crops = P.crop(frame, det, scale=1.0, crop_size=crop_size, bgr=bgr)
+        bbox_scale = torch.as_tensor(det[:, 2] / 200.0, dtype=torch.float32).to(dev)
+        bbox_center = torch.as_tensor(det[:, :2], dtype=torch.float32).to(dev)
+        img_h = torch.full((n,), float(H), dtype=torch.float32, device=dev)
+        img_w = torch.full((n,), float(W), dtype=torch.float32, device=dev)
+        out = self.hmr(crops, R.expand(n, 3, 3).contiguous(), K.expand(n, 3, 3).contiguous(), bbox_scale, bbox_center, img_w, img_h)
+        out = dict(out)
+        out['cam_angles'] = angles.expand(n, 3)
+        out['inp_images'] = crops
+        return out
+
     def launches_per_step(self):
         """Kernels of libspecb200 enqueued by one step (trunk x2 + both tails + decode)."""
         return self.camcalib.backbone.last_launches() + 2 + self.hmr.last_launches()
