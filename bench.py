@@ -230,9 +230,11 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # per-step spread (diagnostic only)
         e0.record()
-        for _ in range(steps):
+        for i in range(steps):
             fn()
+            marks[i].record()
         if gatherer is not None:
             gatherer.flush()                                       # the last gather completes inside the timed region
         e1.record()
@@ -240,6 +242,8 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        per = sorted(a_.elapsed_time(b_) for a_, b_ in zip([e0] + marks[:-1], marks))
+        timed.step_ms = {'min': per[0], 'median': per[len(per) // 2], 'max': per[-1]}
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)             # max over ranks
         return ms.item()
@@ -259,6 +263,7 @@ def run_ours(a):
     if rank == 0:
         sampler.start()
     total_ms = timed(step, a.steps, a.warmup)
+    step_spread = dict(timed.step_ms)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / a.steps
     value = world * B * a.steps / (total_ms * 1e-3)
@@ -353,7 +358,7 @@ def run_ours(a):
                    'sample': f'{a.cpu_sample}-image batches x2 of the same workload, fp32 PyTorch oracle (oracle/), {cores} threads'}
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
-            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_per_step, 'step_ms_spread': step_spread, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': a.precision, 'data': 'synthetic',
             'config': {'workload': f'SPEC full forward (CamCalib resnet50 -> (R,K) -> HMR {a.backbone} -> SMPL -> projection), 224x224, batch {B}/GPU, random weights',
                        'backbone': a.backbone, 'batch_per_gpu': B, 'global_batch': B * world, 'cuda_graph': not a.no_graph,

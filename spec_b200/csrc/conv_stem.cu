@@ -14,6 +14,7 @@
 // The CTA is sequential per tile; two to three co-resident CTAs per SM (93 KB smem each) overlap the phases.
 #include "common.cuh"
 #include "internal.h"
+#include <string>
 #include <stdlib.h>
 
 namespace sb {
@@ -209,15 +210,21 @@ constexpr int STP_OFF_A = 0;                                   // 2 x 49152
 constexpr int STP_OFF_B = 2 * ST_A_BYTES;                      // 24576
 constexpr int STP_OFF_STAGE = STP_OFF_B + ST_B_BYTES;          // 2 x 16384
 constexpr int STP_OFF_PATCH = STP_OFF_STAGE + 2 * ST_STAGE_BYTES;   // 2 x 6144
-constexpr int STP_OFF_BIAS = STP_OFF_PATCH + 2 * 6144;
-constexpr int STP_OFF_BAR = STP_OFF_BIAS + 256;                // b, a_full[2], a_empty[2], t_full[2], t_empty[2], tmem ptr
+constexpr int STP_RING = 4;                                     // fp32 input patches in flight (TMA), 3 tiles ahead
+constexpr int STP_RP = 40;                                      // ring row pitch (floats) = TMA box width: 37 used
+constexpr int STP_BOX_BYTES = 3 * ST_PR * STP_RP * 4;           // 10080: one 40 x 21 x 3 fp32 box
+constexpr int STP_RING_BYTES = 64 * STP_RP * 4;                 // slot pitch (10240)
+constexpr int STP_OFF_RING = STP_OFF_PATCH + 2 * 6144;
+constexpr int STP_OFF_BIAS = STP_OFF_RING + STP_RING * STP_RING_BYTES;
+constexpr int STP_OFF_BAR = STP_OFF_BIAS + 256;                // b, a_full[2], a_empty[2], t_full[2], t_empty[2], tmem ptr, ring_full[4]
 constexpr int STP_DYN_BYTES = STP_OFF_BAR + 128 + 1024;
 static_assert(STP_DYN_BYTES <= 232448, "stem: shared memory");
 
 template <typename T>
 __global__ void __launch_bounds__(STP_THREADS, 1)
-conv_stem7p_kernel(const float* __restrict__ img, const float* __restrict__ bias, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_out, int N, int H, int W, int tiles_h, int tiles_w, int total_tiles)
+conv_stem7p_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __restrict__ bias,
+                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
+                   int tiles_h, int tiles_w, int total_tiles)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -230,10 +237,12 @@ conv_stem7p_kernel(const float* __restrict__ img, const float* __restrict__ bias
     const uint32_t bar_b = sbase + STP_OFF_BAR;
     const uint32_t bar_afull = bar_b + 8, bar_aempty = bar_b + 24, bar_tfull = bar_b + 40, bar_tempty = bar_b + 56;
     volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sgen + STP_OFF_BAR + 72);
+    const uint32_t bar_ring = bar_b + 80;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         mbar_init(bar_b, 1);
+        for (int i = 0; i < STP_RING; ++i) mbar_init(bar_ring + i * 8, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_afull + i * 8, 8);                    // one arrival per builder warp
             mbar_init(bar_aempty + i * 8, 1);                   // tcgen05.commit
@@ -256,42 +265,45 @@ conv_stem7p_kernel(const float* __restrict__ img, const float* __restrict__ bias
     if (warp >= 4 && warp < 12) {
         // ================= builders
         const int wb = warp - 4, bt = tid - 128;
-        const size_t plane = static_cast<size_t>(H) * W;
-        float pre[16];
-        auto prefetch = [&](int tile) {
+        const uint32_t ring_base = sbase + STP_OFF_RING;
+        const float* ring_gen = reinterpret_cast<const float*>(sgen + STP_OFF_RING);
+        // The fp32 image is the only HBM read of this kernel and one tile's patch is under 10 KB: with a single tile in
+        // flight per SM (register prefetch, first version) the builders waited a full memory latency per tile.  One
+        // builder thread therefore keeps the patches of the next THREE tiles in flight as 4-D TMA boxes (40 x 21 x 3 fp32,
+        // out-of-image pixels zero-filled by the TMA unit = the conv's padding) into a ring of four slots.
+        // (4-byte cp.async was tried for this ring and is element-rate bound: 0.36 ms vs 0.27 ms.)
+        auto issue = [&](int tile, uint32_t slot) {
+            if (tile >= total_tiles) return;
             const int tw = tile % tiles_w;
             const int th = (tile / tiles_w) % tiles_h;
             const int n = tile / (tiles_w * tiles_h);
-            const int ih0 = 2 * th * ST_TH - 3, iw0 = 2 * tw * ST_TW - 3;
-            const float* src = img + static_cast<size_t>(n) * 3 * plane;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int row = wb + 8 * k;
-                const int c = row >= 42 ? 2 : (row >= 21 ? 1 : 0);
-                const int r = row - c * 21;
-                const int ih = ih0 + r;
-                const bool rok = row < 63 && static_cast<unsigned>(ih) < static_cast<unsigned>(H);
-                const float* rp = src + c * plane + static_cast<size_t>(rok ? ih : 0) * W;
-                const int iwa = iw0 + lane, iwb = iw0 + lane + 32;
-                pre[2 * k] = (rok && static_cast<unsigned>(iwa) < static_cast<unsigned>(W)) ? __ldg(rp + iwa) : 0.f;
-                pre[2 * k + 1] = (rok && lane < ST_PC - 32 && static_cast<unsigned>(iwb) < static_cast<unsigned>(W)) ? __ldg(rp + iwb) : 0.f;
-            }
+            mbar_arrive_expect_tx(bar_ring + slot * 8, STP_BOX_BYTES);
+            // the box start must be 16-byte aligned in global memory (tools/tma_img_test.cu): load from x = 32 tw - 4, one
+            // column left of the patch, and read the ring at column + 1
+            tma_load_4d(ring_base + slot * STP_RING_BYTES, &tmap_img, bar_ring + slot * 8, 2 * tw * ST_TW - 4, 2 * th * ST_TH - 3, 0, n);
         };
-        if (static_cast<int>(blockIdx.x) < total_tiles) prefetch(blockIdx.x);
+        if (bt == 0) {
+            tma_prefetch_desc(&tmap_img);
+            for (int d = 0; d < STP_RING - 1; ++d) issue(static_cast<int>(blockIdx.x + d * gridDim.x), d);
+        }
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            const uint32_t slot = it % STP_RING;
             T* patch = patch0 + s * (6144 / 2);
+            mbar_wait(bar_ring + slot * 8, (it / STP_RING) & 1);   // this tile's fp32 patch has landed
+            const float* mine = ring_gen + slot * (STP_RING_BYTES / 4) + wb * STP_RP + lane + 1;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int row = wb + 8 * k;
                 if (row < 63) {
-                    patch[row * ST_PP + lane] = DT<T>::from_f(pre[2 * k]);
-                    if (lane < ST_PC - 32) patch[row * ST_PP + lane + 32] = DT<T>::from_f(pre[2 * k + 1]);
+                    patch[row * ST_PP + lane] = DT<T>::from_f(mine[k * 8 * STP_RP]);
+                    if (lane < ST_PC - 32) patch[row * ST_PP + lane + 32] = DT<T>::from_f(mine[k * 8 * STP_RP + 32]);
                 }
             }
             named_bar_sync(2, 256);                             // patch[s] complete; also orders the reuse of patch[s ^ 1]
-            if (tile + static_cast<int>(gridDim.x) < total_tiles) prefetch(tile + gridDim.x);
+            // every builder has read ring slots <= it: the slot of tile it-1 may be refilled (tile it+3)
+            if (bt == 0) issue(tile + (STP_RING - 1) * static_cast<int>(gridDim.x), (it + STP_RING - 1) % STP_RING);
             mbar_wait(bar_aempty + s * 8, ph ^ 1);              // the MMAs of tile it-2 have consumed A[s]
             {
                 const int t = bt & 127, half = bt >> 7;
@@ -393,6 +405,32 @@ conv_stem7p_kernel(const float* __restrict__ img, const float* __restrict__ bias
     }
 }
 
+// 4-D tiled TMA descriptor over the fp32 NCHW image: box = 40 x 21 x 3 x 1 (one stem tile's input patch), no swizzle,
+// out-of-bounds elements read as zero (= the convolution's zero padding).
+static bool make_tmap_image_f32(CUtensorMap* m, const float* img, int W, int H, int N) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) != cudaSuccess || !q) {
+            set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+            return false;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(q);
+    }
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), 3, static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * 4, static_cast<cuuint64_t>(H) * W * 4, static_cast<cuuint64_t>(H) * W * 12};
+    cuuint32_t box[4] = {STP_RP, ST_PR, 3, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(img), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(image) failed (code " + std::to_string(static_cast<int>(r)) + ")"); return false; }
+    return true;
+}
+
 bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N, int H, int W, int Ho, int Wo, int prec,
                        cudaStream_t s) {
     if (!w.has_tmap || !w.stem7) { set_error("conv_stem7: weights not packed for the stem kernel"); return false; }
@@ -407,9 +445,11 @@ bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N,
     if (total > 0x7fffffffLL) { set_error("conv_stem7: too many tiles"); return false; }
     static int v1 = -1;                                          // SPECB200_STEM_V1=1: the first (non-pipelined) kernel, for A/B runs
     if (v1 < 0) { const char* e = getenv("SPECB200_STEM_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
-    if (!v1) {
-        CUtensorMap tmap_out;
+    // the TMA-fed kernel needs 16-byte aligned image rows (W % 4 == 0); other widths keep the first kernel
+    if (!v1 && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+        CUtensorMap tmap_out, tmap_img;
         if (!make_tmap_nhwc(&tmap_out, out, 64, Wo, Ho, N, ST_TW, ST_TH)) return false;
+        if (!make_tmap_image_f32(&tmap_img, img, W, H, N)) return false;
         static DeviceOnce attr_p;
         if (attr_p.need()) {
             if (!check_cuda(cudaFuncSetAttribute(conv_stem7p_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STP_DYN_BYTES), "stem attr")) return false;
@@ -417,9 +457,9 @@ bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N,
         }
         const unsigned gridp = static_cast<unsigned>(total < num_sms ? total : num_sms);
         if (prec == PREC_BF16)
-            conv_stem7p_kernel<__nv_bfloat16><<<gridp, STP_THREADS, STP_DYN_BYTES, s>>>(img, w.bias, w.tmap_b, tmap_out, N, H, W, tiles_h, tiles_w, static_cast<int>(total));
+            conv_stem7p_kernel<__nv_bfloat16><<<gridp, STP_THREADS, STP_DYN_BYTES, s>>>(tmap_img, w.bias, w.tmap_b, tmap_out, tiles_h, tiles_w, static_cast<int>(total));
         else if (prec == PREC_F16)
-            conv_stem7p_kernel<__half><<<gridp, STP_THREADS, STP_DYN_BYTES, s>>>(img, w.bias, w.tmap_b, tmap_out, N, H, W, tiles_h, tiles_w, static_cast<int>(total));
+            conv_stem7p_kernel<__half><<<gridp, STP_THREADS, STP_DYN_BYTES, s>>>(tmap_img, w.bias, w.tmap_b, tmap_out, tiles_h, tiles_w, static_cast<int>(total));
         else { set_error("conv_stem7: 16-bit precisions only"); return false; }
         return check_cuda(cudaGetLastError(), "conv_stem7p launch");
     }
