@@ -43,9 +43,11 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region through NVML (in-process, ~50 us per sample:
-    polling the nvidia-smi binary at 10 Hz was measured to slow the timed loop by ~20 %).  Falls back to a slow
-    nvidia-smi poll when pynvml is missing."""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML, inline from the timing loop (``sample()`` is
+    called once in the middle of the K timed steps, while the GPU is busy with the steps already enqueued).  Every NVML query
+    stalls the GPU for a moment: polling the nvidia-smi binary at 10 Hz slowed the timed loop by ~20 %, and a 20 Hz in-process
+    sampler thread showed up as ~3 ms outlier steps (``step_ms_spread``), so exactly one sample is taken per timed region
+    (plus one every 64 steps for long runs).  Falls back to a slow nvidia-smi poll thread when pynvml is missing."""
     BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
@@ -53,19 +55,21 @@ class ClockSampler:
         self._stop = threading.Event()
         self.t = None
         self.mode = None
+        self._nvml = None
 
-    def _nvml_loop(self, h, nv):
-        while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons') \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for name, bit in self.BITS:
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(0.05)
+    def sample(self):
+        if self._nvml is None:
+            return
+        h, nv = self._nvml
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons') \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in self.BITS:
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def _smi_loop(self):
         q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
@@ -91,11 +95,11 @@ class ClockSampler:
             h = nv.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             self.mode = 'nvml'
-            self.t = threading.Thread(target=self._nvml_loop, args=(h, nv), daemon=True)
+            self._nvml = (h, nv)
         except Exception:
             self.mode = 'nvidia-smi'
             self.t = threading.Thread(target=self._smi_loop, daemon=True)
-        self.t.start()
+            self.t.start()
 
     def stop(self):
         self._stop.set()
@@ -217,7 +221,7 @@ def run_ours(a):
             return gatherer.submit(rec)                           # the ONE collective of the data path; overlaps the next step
         return rec
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, mid=None):
         t_w = time.perf_counter()
         n_w = 0
         while n_w < warmup or time.perf_counter() - t_w < 0.4:     # >= W steps AND ~0.4 s so the clocks have ramped
@@ -235,6 +239,8 @@ def run_ours(a):
         for i in range(steps):
             fn()
             marks[i].record()
+            if mid is not None and i % 64 == min(steps // 2, 32):
+                mid()                                              # clocks / throttle reasons, inside the timed region
         if gatherer is not None:
             gatherer.flush()                                       # the last gather completes inside the timed region
         e1.record()
@@ -242,8 +248,9 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        per = sorted(a_.elapsed_time(b_) for a_, b_ in zip([e0] + marks[:-1], marks))
-        timed.step_ms = {'min': per[0], 'median': per[len(per) // 2], 'max': per[-1]}
+        raw = [a_.elapsed_time(b_) for a_, b_ in zip([e0] + marks[:-1], marks)]
+        per = sorted(raw)
+        timed.step_ms = {'min': per[0], 'median': per[len(per) // 2], 'max': per[-1], 'argmax': raw.index(per[-1])}
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)             # max over ranks
         return ms.item()
@@ -262,7 +269,7 @@ def run_ours(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms = timed(step, a.steps, a.warmup)
+    total_ms = timed(step, a.steps, a.warmup, mid=sampler.sample if rank == 0 else None)
     step_spread = dict(timed.step_ms)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / a.steps
