@@ -171,7 +171,7 @@ def run_reference(a):
     sample = a.cpu_sample
     ips, ms, cores = time_oracle(a.backbone, sample, a.steps, a.warmup)
     desc = f'{sample} of {a.batch} images per step (bounded CPU sample), fp32 PyTorch oracle, {cores} threads'
-    print(json.dumps({
+    _emit({
         'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
         'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
@@ -180,7 +180,7 @@ def run_reference(a):
         'cpu_baseline': {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
         'e2e': {'value': ips, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-    }))
+    })
 
 
 # =============================================================================================== our arm
@@ -388,14 +388,39 @@ def run_ours(a):
                          'step_frac_of_peak': (world * 0 + conv_flops) / (ms_per_step * 1e-3) / 1e12 / peaks['tf_sustained']},
             'cpu_baseline': cpu,
         }
-        print(json.dumps(out))
+        _emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return out
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when the
+    first communicator is created), so everything that goes to fd 1 from here on is sent to stderr and the JSON line is
+    written to the saved descriptor by ``_emit``."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
