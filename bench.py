@@ -197,6 +197,7 @@ def run_ours(a):
         raise SystemExit(f'--gpus {a.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = sb.bind_process_to_gpu_numa(local)                      # pinned staging buffers on the GPU's NUMA node
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -360,6 +361,12 @@ def run_ours(a):
         # ---- cpu baseline (bounded sample, rank 0, N=1 only)
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
+            if numa.get('bound'):                                  # the CPU baseline may use every host core again:
+                for tid in os.listdir('/proc/self/task'):          # reset every thread (OpenMP workers inherited the mask)
+                    try:
+                        os.sched_setaffinity(int(tid), numa['previous'])
+                    except OSError:
+                        pass
             ips, _, cores = time_oracle(a.backbone, a.cpu_sample, 2, 1)
             cpu = {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                    'sample': f'{a.cpu_sample}-image batches x2 of the same workload, fp32 PyTorch oracle (oracle/), {cores} threads'}
@@ -369,6 +376,7 @@ def run_ours(a):
             'dtype': a.precision, 'data': 'synthetic',
             'config': {'workload': f'SPEC full forward (CamCalib resnet50 -> (R,K) -> HMR {a.backbone} -> SMPL -> projection), 224x224, batch {B}/GPU, random weights',
                        'backbone': a.backbone, 'batch_per_gpu': B, 'global_batch': B * world, 'cuda_graph': not a.no_graph,
+                       'numa': {k: v for k, v in numa.items() if k != 'previous'},
                        'l2': 'inputs 154 MB/step/GPU > 126 MB L2, no explicit flush (weights stay L2-resident as in steady-state serving)',
                        'parallelism': f'dp{world} (batch shard + one all-gather of 85,176 B/image records)' if world > 1 else 'single GPU'},
             'clocks': clocks,
@@ -378,8 +386,8 @@ def run_ours(a):
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
                          'frac': achieved / peaks['tf_sustained'],
                          # dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step (2 trunks), from the
-                         # committed ncu --set full capture profiles/ncu_r01b.md (12.99 GB per trunk; resnet50, B=256, bf16)
-                         'traffic': 25.98e9 if (a.backbone == 'resnet50' and B == 256 and a.precision == 'bf16') else None,
+                         # committed ncu --set full capture profiles/ncu_r01d.md (14.75 GB per trunk; resnet50, B=256, bf16)
+                         'traffic': 29.5e9 if (a.backbone == 'resnet50' and B == 256 and a.precision == 'bf16') else None,
                          'algorithmic_bytes': conv_bytes,
                          'kernel': 'tcgen05 implicit-GEMM conv family: conv_tcp/conv_tcp2 (cta_group::2)/conv_tc/conv3x3_halo/conv_stem7, %d launches/step' % n_conv,
                          'how': 'sum of conv FLOPs of both trunks / sum of per-launch CUDA-event times (specb200_trunk_profile, eager, same stream)',

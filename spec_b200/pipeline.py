@@ -199,3 +199,35 @@ def shard_range(total, rank, world):
     per = (total + world - 1) // world
     lo = min(rank * per, total)
     return lo, min(lo + per, total)
+
+
+def bind_process_to_gpu_numa(device_index):
+    """Pin the calling process to the CPUs that are local to GPU ``device_index`` (sysfs ``local_cpulist`` of its PCI function)
+    so that the pinned host staging buffers it allocates afterwards land on the GPU's NUMA node.  A serving / eval process
+    that feeds 19 GB/s of images to one B200 (31 k img/s x 602 KB) through staging buffers on the REMOTE socket was measured
+    at ~22 k img/s end to end instead of ~31 k.  Returns a dict describing what was done (for logs); never raises."""
+    import os
+    info = {'bound': False}
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        idx = int(vis.split(',')[device_index]) if vis and vis.split(',')[0].isdigit() else device_index
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(':', 1)
+        dev_dir = f'/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}'
+        cpus = set()
+        for part in open(dev_dir + '/local_cpulist').read().strip().split(','):
+            if part:
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        local = allowed & cpus
+        info.update(pci=bus, numa_node=open(dev_dir + '/numa_node').read().strip(), local_cpus=len(cpus), allowed_cpus=len(allowed))
+        if local and local != allowed:
+            os.sched_setaffinity(0, local)
+            info.update(bound=True, cpus=len(local), previous=sorted(allowed))
+    except Exception as e:                                   # no sysfs / no NVML / restricted container: leave the affinity alone
+        info['error'] = repr(e)[:120]
+    return info
