@@ -7,7 +7,9 @@ and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import
 it.  The product (``spec_b200``) never does, and fails loudly without its CUDA
 library.
 
-PARITY STATUS: *parity unpinned* for everything except the ResNet trunk.
+PARITY STATUS: *parity unpinned* for everything except the ResNet trunk and the
+INPUT SIDE (oracle/preprocess.py: person crops and the CamCalib resize are pinned
+bit-exactly against cv2 / Pillow / torchvision, which ARE installed here).
 The reference keeps the arithmetic of this path in two un-vendored third-party
 packages -- ``pare`` (git+https://github.com/mkocabas/PARE.git, NO commit
 pinned, /root/reference/requirements.txt:28) and ``smplx==0.1.28``
