@@ -139,22 +139,31 @@ linear_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict_
     const int ty = tid >> 4, tx = tid & 15;                 // rows ty*2.., cols tx*4..
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 
-    for (int k0 = 0; k0 < K; k0 += LN_BK) {
-        {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + a_r < M && k0 + a_k < K)
-                v = *reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + a_r) * lda + k0 + a_k);
-            As[a_k + 0][a_r] = v.x; As[a_k + 1][a_r] = v.y; As[a_k + 2][a_r] = v.z; As[a_k + 3][a_r] = v.w;
-        }
+    // register double-buffering: the global loads of k-block i+1 are in flight while k-block i is multiplied (the grid of the
+    // CamCalib GEMM is only 96 CTAs, so nothing else hides the load latency)
+    auto load_tiles = [&](int k0, float4& va, float4 (&vw)[2]) {
+        va = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + a_r < M && k0 + a_k < K)
+            va = *reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + a_r) * lda + k0 + a_k);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int w_r = (tid >> 3) + h * 32;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            vw[h] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (n0 + w_r < N && k0 + a_k < K)
-                v = *reinterpret_cast<const float4*>(W + static_cast<size_t>(n0 + w_r) * ldw + k0 + a_k);
-            Ws[a_k + 0][w_r] = v.x; Ws[a_k + 1][w_r] = v.y; Ws[a_k + 2][w_r] = v.z; Ws[a_k + 3][w_r] = v.w;
+                vw[h] = *reinterpret_cast<const float4*>(W + static_cast<size_t>(n0 + w_r) * ldw + k0 + a_k);
+        }
+    };
+    float4 va, vw[2];
+    load_tiles(0, va, vw);
+    for (int k0 = 0; k0 < K; k0 += LN_BK) {
+        As[a_k + 0][a_r] = va.x; As[a_k + 1][a_r] = va.y; As[a_k + 2][a_r] = va.z; As[a_k + 3][a_r] = va.w;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int w_r = (tid >> 3) + h * 32;
+            Ws[a_k + 0][w_r] = vw[h].x; Ws[a_k + 1][w_r] = vw[h].y; Ws[a_k + 2][w_r] = vw[h].z; Ws[a_k + 3][w_r] = vw[h].w;
         }
         __syncthreads();
+        if (k0 + LN_BK < K) load_tiles(k0 + LN_BK, va, vw);
 #pragma unroll
         for (int k = 0; k < LN_BK; ++k) {
             const float2 a = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
