@@ -101,55 +101,9 @@ __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, in
 // (A column-strip variant -- one thread walks down the rows carrying the horizontal 3-max, 6 instead of 9 reads per
 // output -- was measured SLOWER, 0.21 vs 0.14 ms at B=256: the serial row walk costs more latency than the re-reads.)
 
-// Two horizontally adjacent outputs per thread: the 3x5 input window is read once (15 vector loads for two outputs instead
-// of 18) and all loads are independent.  Requires an even Wo.  Opt-in (SPECB200_MAXPOOL2=1) until measured.
-template <typename T>
-__global__ void maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int Ho, int Wo) {
-    constexpr int V = V16<T>::N;
-    const int cv = C / V, wo2 = Wo / 2;
-    const long long total = static_cast<long long>(N) * Ho * wo2 * cv;
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = static_cast<int>(i % cv) * V;
-    long long t = i / cv;
-    const int ow = static_cast<int>(t % wo2) * 2; t /= wo2;
-    const int oh = static_cast<int>(t % Ho);
-    const long long n = t / Ho;
-    float m0[V], m1[V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) { m0[e] = -INFINITY; m1[e] = -INFINITY; }
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        const int ih = oh * 2 - 1 + dy;
-        if (ih < 0 || ih >= H) continue;
-#pragma unroll
-        for (int dx = 0; dx < 5; ++dx) {
-            const int iw = ow * 2 - 1 + dx;
-            if (iw < 0 || iw >= W) continue;
-            float f[V];
-            V16<T>::load(in + ((n * H + ih) * W + iw) * C + c, f);
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                if (dx <= 2) m0[e] = fmaxf(m0[e], f[e]);
-                if (dx >= 2) m1[e] = fmaxf(m1[e], f[e]);
-            }
-        }
-    }
-    T* o = out + ((n * Ho + oh) * Wo + ow) * C + c;
-    V16<T>::store(o, m0);
-    V16<T>::store(o + C, m1);
-}
-
+// (Two horizontally adjacent outputs per thread -- a 3x5 window read once, 15 loads for two outputs instead of 18 -- was
+// also measured SLOWER, 0.162 vs 0.139 ms: half the threads, less latency hiding.)
 bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int prec, cudaStream_t s) {
-    static int two = -1;
-    if (two < 0) { const char* e = getenv("SPECB200_MAXPOOL2"); two = (e && e[0] == '1') ? 1 : 0; }
-    if (two && (Wo % 2) == 0) {
-        SB_DISPATCH_PREC(prec, {
-            const long long total = static_cast<long long>(N) * Ho * (Wo / 2) * (C / V16<T>::N);
-            maxpool2_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, Ho, Wo);
-        });
-        return check_cuda(cudaGetLastError(), "maxpool");
-    }
     SB_DISPATCH_PREC(prec, {
         const long long total = static_cast<long long>(N) * Ho * Wo * (C / V16<T>::N);
         maxpool_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, Ho, Wo);
