@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -326,6 +327,9 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
                     p.out_ld = t->buf_ch[o.dst]; p.out_coff = o.dst_coff;
                     p.res_ld = o.src2 >= 0 ? t->buf_ch[o.src2] : 0;
                     p.relu = o.relu;
+                    static int split_prod = -1;          // SPECB200_SPLIT_PRODUCER=1: second TMA producer thread for the weight tiles (experiment)
+                    if (split_prod < 0) { const char* e = getenv("SPECB200_SPLIT_PRODUCER"); split_prod = (e && e[0] == '1') ? 1 : 0; }
+                    p.split_producer = split_prod;
                     if (pair) { p.W /= 2; p.Wo /= 2; p.M /= 2; p.Cin = 64; p.Cout = 64; p.out_ld = 64; p.res_ld = o.src2 >= 0 ? 64 : 0; }
                     const bool ok = (t->prec == PREC_F32) ? conv_f32_launch(p, cw, s)
                                     : (conv_halo_applicable(p, cw) ? conv_halo_launch(p, cw, t->prec, s) : conv_tc_launch(p, cw, t->prec, s));

@@ -486,7 +486,7 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
                     const uint32_t s = kc % STAGES, it = kc / STAGES;
                     mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
                     mbar_arrive_expect_tx(bar_full + s * 8, tx_bytes);
-                    tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
+                    if (!p.split_producer) tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
                     if constexpr (A_MODE == A_TILED) {
                         tma_load_2d(a_base + s * A_STAGE_BYTES, &maps.a, bar_full + s * 8, kb * TILE_K, m_tile * TILE_M);
                     } else {
@@ -497,6 +497,20 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
                         tma_load_im2col_4d(a_base + s * A_STAGE_BYTES, &maps.a, bar_full + s * 8, c0, pw, ph, pn,
                                            static_cast<uint16_t>(kwi), static_cast<uint16_t>(khi));
                     }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3 && p.split_producer) {
+        // ================= second producer (experiment): the weight tiles, same stage / phase sequence as warp 0
+        if (lane == 0) {
+            uint32_t kc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % n_tiles) * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+                    const uint32_t s = kc % STAGES, it = kc / STAGES;
+                    mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
+                    tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
                 }
             }
         }

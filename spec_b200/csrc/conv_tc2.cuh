@@ -104,7 +104,7 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
                     mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);                  // own stage released (multicast commit)
                     const uint32_t lead_full = mapa_u32(bar_full + s * 8, 0);
                     mbar_arrive_expect_tx_cluster(lead_full, tx_bytes);
-                    tma_load_2d_2sm(b_base + s * L::B_STAGE_BYTES, &maps.b, lead_full, kb * TILE_K, nrow0);
+                    if (!p.split_producer) tma_load_2d_2sm(b_base + s * L::B_STAGE_BYTES, &maps.b, lead_full, kb * TILE_K, nrow0);
                     if constexpr (A_MODE == A_TILED) {
                         tma_load_2d_2sm(a_base + s * A_STAGE_BYTES, &maps.a, lead_full, kb * TILE_K, m_tile * TILE_M);
                     } else {
@@ -115,6 +115,22 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
                         tma_load_im2col_4d_2sm(a_base + s * A_STAGE_BYTES, &maps.a, lead_full, c0, pw, ph, pn,
                                                static_cast<uint16_t>(kwi), static_cast<uint16_t>(khi));
                     }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3 && p.split_producer) {
+        // ================= second producer (experiment): the weight half-tiles, same stage / phase sequence as warp 0.
+        // Bytes that land before warp 0 has armed the barrier only make the tx-count transiently negative.
+        if (lane == 0) {
+            uint32_t kc = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+                const int n_tile = tile % n_tiles;
+                const int nrow0 = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+                for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+                    const uint32_t s = kc % STAGES, it = kc / STAGES;
+                    mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
+                    tma_load_2d_2sm(b_base + s * L::B_STAGE_BYTES, &maps.b, mapa_u32(bar_full + s * 8, 0), kb * TILE_K, nrow0);
                 }
             }
         }
