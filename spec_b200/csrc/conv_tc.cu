@@ -131,6 +131,21 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
         const int t = q4 * 32 + lane;                            // tile row == TMEM lane
         const long long r = static_cast<long long>(m_tile) * TILE_M + t;
         const bool row_ok = r < p.M;
+        // ---------------- optional second TMA producer (experiment, ConvParams::split_producer): warp 6 issues the weight tiles
+        // while warp 4 issues A; its epilogue share starts afterwards (every load is issued long before the last MMA retires)
+        if constexpr (A_MODE == A_TILED || A_MODE == A_IM2COL) {
+            if (p.split_producer && warp == 6) {
+                if (lane == 0) {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        const int s = kb % STAGES;
+                        const int it = kb / STAGES;
+                        mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
+                        tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
+                    }
+                }
+                __syncwarp();
+            }
+        }
         // ---------------- A producer (software im2col)
         if (grp == 0)
         if constexpr (A_MODE == A_GATHER || A_MODE == A_STEM) {
@@ -329,7 +344,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
                 const int it = kb / STAGES;
                 mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
                 mbar_arrive_expect_tx(bar_full + s * 8, tx_bytes);
-                tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
+                if (!(p.split_producer && (A_MODE == A_TILED || A_MODE == A_IM2COL)))
+                    tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
                 if constexpr (A_MODE == A_TILED) {
                     tma_load_2d(a_base + s * A_STAGE_BYTES, &maps.a, bar_full + s * 8, kb * TILE_K, m_tile * TILE_M);
                 } else if constexpr (A_MODE == A_IM2COL) {
