@@ -208,3 +208,41 @@ def test_compiled_program_equals_oracle_on_cpu(backbone):
     assert got.shape == want.shape
     err = (got - want).abs().max().item()
     assert err < 2e-3 * max(1.0, want.abs().max().item()), err
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/specb200.h must be consumable from C (extern "C", plain pointers and sizes, no C++ or torch types): compile a C
+    translation unit that references every declared entry point with gcc -std=c99 -pedantic, link it against libspecb200.so and
+    run it (host-only calls: ABI version, an error path, the crop-transform arithmetic)."""
+    import re
+    import shutil
+    import subprocess
+    from spec_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    _lib.lib()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, 'include', 'specb200.h')).read()
+    names = sorted(set(re.findall(r'\b(specb200_[a-z0-9_]+)\s*\(', hdr)))
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS)
+    src = ['#include "specb200.h"', '#include <stdio.h>', '#include <math.h>', 'typedef void (*fn_t)(void);', 'int main(void) {', '    fn_t syms[] = {']
+    src += [f'        (fn_t)&{n},' for n in names]
+    src += ['    };',
+            '    double box[4] = {100.0, 60.0, 64.0, 64.0}, trans[6], inv[6];',
+            '    if (specb200_abi_version() != 1) return 2;',
+            '    if (specb200_preproc_crop_transforms(box, 1, 1.0, 64, trans, inv) != 0) return 3;',
+            '    if (fabs(trans[0] - 1.0) > 1e-9 || fabs(trans[2] - (32.0 - 100.0)) > 1e-9 || fabs(inv[5] - (60.0 - 32.0)) > 1e-9) return 4;',
+            '    if (specb200_preproc_crop_transforms(0, 1, 1.0, 64, trans, inv) == 0) return 5;     /* error path */',
+            '    if (specb200_last_error()[0] == 0) return 6;',
+            '    printf("%d symbols\\n", (int)(sizeof(syms) / sizeof(syms[0])));',
+            '    return 0;', '}']
+    c = tmp_path / 'use_abi.c'
+    c.write_text('\n'.join(src))
+    exe = tmp_path / 'use_abi'
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(['gcc', '-std=c99', '-pedantic', '-Wall', '-Werror', '-I', os.path.join(root, 'include'), str(c), '-o', str(exe),
+                        '-L', libdir, '-l:libspecb200.so', f'-Wl,-rpath,{libdir}', '-lm'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.strip() == f'{len(names)} symbols'
