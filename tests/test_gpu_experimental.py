@@ -1,0 +1,23 @@
+"""Opt-in kernel variants that were measured faster but could not be parity-tested before the GPU budget of round 1 ran out
+(profiles/round2_plan.md).  Each runs the conv-kernel and whole-path 16-bit parity tests in a subprocess with the switch set
+(the switches are read once per process).  xfail(strict=False): a failure here must not turn the suite red -- the default path does
+not use these variants -- and an XPASS is the signal to promote the variant to the default."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason='experimental opt-in variant, not yet validated on hardware')
+@pytest.mark.parametrize('switch', ['SPECB200_SPLIT_PRODUCER'])
+def test_opt_in_variant_keeps_parity(switch):
+    env = dict(os.environ)
+    env[switch] = '1'
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-x', '-q',
+                        '-k', 'conv_kernels or lowp_parity or golden or ragged or hrnet_bf16'],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
