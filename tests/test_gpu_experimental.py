@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason='experimental opt-in variant, not yet validated on hardware')
-@pytest.mark.parametrize('switch', ['SPECB200_SPLIT_PRODUCER'])
+@pytest.mark.parametrize('switch', ['SPECB200_SPLIT_PRODUCER', 'SPECB200_MCAST_B'])
 def test_opt_in_variant_keeps_parity(switch):
     env = dict(os.environ)
     env[switch] = '1'
