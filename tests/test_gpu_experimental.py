@@ -1,7 +1,10 @@
 """Opt-in kernel variants that were measured faster but could not be parity-tested before the GPU budget of round 1 ran out
 (profiles/round2_plan.md).  Each runs the conv-kernel and whole-path 16-bit parity tests in a subprocess with the switch set
-(the switches are read once per process).  xfail(strict=False): a failure here must not turn the suite red -- the default path does
-not use these variants -- and an XPASS is the signal to promote the variant to the default."""
+(the switches are read once per process).  They only run when SPECB200_RUN_EXPERIMENTAL=1 -- code that has never executed on
+hardware must not run inside the round-end validation, where a hang would cost the real tests and the bench their GPU -- and are
+xfail(strict=False): an XPASS is the signal to promote the variant to the default.
+
+    SPECB200_RUN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q"""
 import os
 import subprocess
 import sys
@@ -12,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get('SPECB200_RUN_EXPERIMENTAL') != '1', reason='set SPECB200_RUN_EXPERIMENTAL=1 to run never-validated kernel variants')
 @pytest.mark.xfail(strict=False, reason='experimental opt-in variant, not yet validated on hardware')
 @pytest.mark.parametrize('switch', ['SPECB200_SPLIT_PRODUCER', 'SPECB200_MCAST_B'])
 def test_opt_in_variant_keeps_parity(switch):
@@ -19,5 +23,5 @@ def test_opt_in_variant_keeps_parity(switch):
     env[switch] = '1'
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-x', '-q',
                         '-k', 'conv_kernels or lowp_parity or golden or ragged or hrnet_bf16'],
-                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+                       capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
