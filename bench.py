@@ -230,12 +230,16 @@ def run_ours(a):
             n_w += 1
             if n_w % 4 == 0:
                 torch.cuda.synchronize(dev)
+        # events are created (and one is recorded once, which is where CUDA really allocates it) BEFORE the bracket, so that
+        # nothing but the record of e0 sits between the synchronize and the first timed step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # per-step spread (diagnostic only)
+        for ev in [e0, e1] + marks:
+            ev.record()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # per-step spread (diagnostic only)
         e0.record()
         for i in range(steps):
             fn()
