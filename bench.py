@@ -230,7 +230,7 @@ def run_ours(a):
             n_w += 1
             if n_w % 4 == 0:
                 torch.cuda.synchronize(dev)
-        # events are created (and one is recorded once, which is where CUDA really allocates it) BEFORE the bracket, so that
+        # events are created (and each recorded once, which is where CUDA really allocates them) BEFORE the bracket, so that
         # nothing but the record of e0 sits between the synchronize and the first timed step
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # per-step spread (diagnostic only)
