@@ -30,7 +30,6 @@ import torch  # noqa: E402
 
 METRIC = 'images/sec SPEC fwd (224^2, b256)'
 UNIT = 'images/s'
-CONV_FLOPS_PER_IMAGE = {'resnet50': 2 * 4087136256}           # SURVEY.md B.1, per trunk
 
 
 def load_peaks():
@@ -43,21 +42,36 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region through NVML, inline from the timing loop (``sample()`` is
-    called once in the middle of the K timed steps, while the GPU is busy with the steps already enqueued).  Every NVML query
-    stalls the GPU for a moment: polling the nvidia-smi binary at 10 Hz slowed the timed loop by ~20 %, and a 20 Hz in-process
-    sampler thread showed up as ~3 ms outlier steps (``step_ms_spread``), so exactly one sample is taken per timed region
-    (plus one every 64 steps for long runs).  Falls back to a slow nvidia-smi poll thread when pynvml is missing."""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML: ``sample()`` -- called once in the middle of
+    the K timed steps, while the GPU is busy with the steps already enqueued -- only WAKES a helper thread, which makes the
+    one NVML query.  The launching thread must never block inside the timed loop: at 8 GPUs (driver's nvidia-smi poller
+    holding NVML) an inline query blocked rank 0's host thread for ~190 ms, its launch queue drained and the all-gather
+    stalled every rank (SCALE_r01.json: one 195 ms step).  Polling is out too: every NVML query perturbs the GPU briefly
+    (10 Hz nvidia-smi: -20 %; a 20 Hz sampler thread: ~3 ms outlier steps), so exactly one query per request.
+    Falls back to a slow nvidia-smi poll thread when pynvml is missing."""
     BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
         self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
         self._stop = threading.Event()
+        self._want = threading.Event()
         self.t = None
         self.mode = None
         self._nvml = None
 
     def sample(self):
+        """Non-blocking: asks the helper thread for one NVML query."""
+        self._want.set()
+
+    def _nvml_loop(self):
+        while True:
+            self._want.wait()
+            self._want.clear()
+            if self._stop.is_set():
+                return
+            self._query()
+
+    def _query(self):
         if self._nvml is None:
             return
         h, nv = self._nvml
@@ -96,6 +110,8 @@ class ClockSampler:
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             self.mode = 'nvml'
             self._nvml = (h, nv)
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
         except Exception:
             self.mode = 'nvidia-smi'
             self.t = threading.Thread(target=self._smi_loop, daemon=True)
@@ -103,6 +119,7 @@ class ClockSampler:
 
     def stop(self):
         self._stop.set()
+        self._want.set()
         if self.t is not None:
             self.t.join(3)
         sm = sorted(self.sm)
@@ -169,6 +186,8 @@ def run_reference(a):
     if rank != 0:
         return                                                  # other ranks exit 0 without work
     sample = a.cpu_sample
+    if a.batch <= 0:
+        a.batch = 256
     ips, ms, cores = time_oracle(a.backbone, sample, a.steps, a.warmup)
     desc = f'{sample} of {a.batch} images per step (bounded CPU sample), fp32 PyTorch oracle, {cores} threads'
     _emit({
@@ -184,10 +203,54 @@ def run_reference(a):
 
 
 # =============================================================================================== our arm
+def host_link_probe(dev, nbytes=128 << 20):
+    """Standalone pinned-host <-> device copy rates (GB/s) and the NUMA node(s) the pinned pages landed on -- printed next to
+    ``e2e`` so that a link-bound e2e number can be told from a pipeline-bound one."""
+    import ctypes
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h.fill_(1)                                                     # touch: pages are placed now
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in (('h2d_gbs', (d, h)), ('d2h_gbs', (h, d))):
+        best = 0.0
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        out[name] = round(best, 2)
+    try:                                                           # move_pages(2) with nodes=NULL reports each page's node
+        libc = ctypes.CDLL(None, use_errno=True)
+        n = 64
+        step = nbytes // n
+        pages = (ctypes.c_void_p * n)(*[(h.data_ptr() + i * step) & ~4095 for i in range(n)])
+        status = (ctypes.c_int * n)()
+        if libc.syscall(279, 0, ctypes.c_ulong(n), pages, None, status, 0) == 0:
+            out['pinned_pages_numa_nodes'] = sorted({int(x) for x in status if x >= 0})
+    except Exception:
+        pass
+    return out
+
+
+def load_ncu_traffic(backbone, batch, precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of ONE step, from the committed ``ncu --set full``
+    summary of the current kernels (profiles/ncu_traffic.json, written by tools/summarize_ncu.py); None when there is no
+    capture for this configuration."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        d = json.load(open(p))
+        e = d.get(f'{backbone}|{batch}|{precision}')
+        return (e['bytes_per_step'], e.get('source')) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 def run_ours(a):
     import torch.distributed as dist
     import spec_b200 as sb
-    from spec_b200.synthetic import synthetic_batch, randomize_module_
+    from spec_b200.synthetic import synthetic_batch, synthetic_camera_matrices, synthetic_smpl_data, synthetic_mean_params, randomize_module_
     from spec_b200.constants import RECORD_FLOATS
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -197,27 +260,44 @@ def run_ours(a):
         raise SystemExit(f'--gpus {a.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    numa = sb.bind_process_to_gpu_numa(local)                      # pinned staging buffers on the GPU's NUMA node
+    numa = sb.bind_process_to_gpu_numa(local)                      # CPU affinity + memory policy: pinned staging on the GPU's node
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    B = a.batch                                                   # per-GPU batch (weak scaling)
+    c4 = a.mode == 'c4'                                            # BASELINE configs[3]: CamCalib bypassed, dataset-supplied (R, K)
+    B = a.batch if a.batch > 0 else (128 if c4 else 256)           # per-GPU batch (weak scaling)
     cc = sb.CameraRegressorNetwork('resnet50')
     randomize_module_(cc.backbone, 1)
-    hmr = sb.HMR(a.backbone, use_cam=True, use_cam_feats=True)
+    hmr = sb.HMR(a.backbone, use_cam=True, use_cam_feats=True, smpl_data=synthetic_smpl_data(0), mean_params=synthetic_mean_params(0))
     randomize_module_(hmr.backbone, 0)
     for m in (cc, hmr):
+        m.eval()
         m.backbone.set_precision(a.precision)
         m.backbone.chunk = a.chunk
         m.to(dev)
     pipe = sb.SPECPipeline(cc, hmr, use_graph=not a.no_graph)
     b = synthetic_batch(B, seed=rank, device=dev)                 # each rank generates its own shard
     args = (b['images'], b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'])
+    if c4:
+        R, K = synthetic_camera_matrices(B, seed=rank, device=dev)        # what CamDataset reads from its npz (cam_dataset.py:617-653)
+        orig_shape = torch.stack([b['img_h'], b['img_w']], 1).long()     # int64, as CamDataset yields it (cam_dataset.py:350,486)
+        c4_rec = torch.empty(B, RECORD_FLOATS, dtype=torch.float32, device=dev)
+        c4_out = {k: (v, RECORD_FLOATS) for k, v in sb.unpack_record(c4_rec).items() if k != 'cam_angles'}
 
-    gatherer = sb.RecordGatherer(B, dev) if world > 1 else None
+    gatherer, gather_desc = (sb.make_gatherer(B, dev) if world > 1 else (None, None))
+
+    @torch.no_grad()
+    def compute(inp=None, bound=False):
+        if c4:                                                     # trainer.py:235-245 call, outputs written into the packed record
+            im = inp['images'] if inp is not None else b['images']
+            hmr(im, R, K, b['bbox_scale'], b['bbox_center'], orig_shape[:, 1], orig_shape[:, 0], _out=c4_out)
+            return c4_rec
+        if inp is None:
+            return pipe.forward_packed(*args)
+        return pipe.forward_packed(inp['images'], inp['bbox_scale'], inp['bbox_center'], inp['img_w'], inp['img_h'], bind_inputs=bound)
 
     def step():
-        rec = pipe.forward_packed(*args)
+        rec = compute()
         if world > 1:
             return gatherer.submit(rec)                           # the ONE collective of the data path; overlaps the next step
         return rec
@@ -245,7 +325,7 @@ def run_ours(a):
             fn()
             marks[i].record()
             if mid is not None and i % 64 == min(steps // 2, 32):
-                mid()                                              # clocks / throttle reasons, inside the timed region
+                mid()                                              # wakes the NVML helper thread; never blocks this thread
         if gatherer is not None:
             gatherer.flush()                                       # the last gather completes inside the timed region
         e1.record()
@@ -276,14 +356,20 @@ def run_ours(a):
         sampler.start()
     total_ms = timed(step, a.steps, a.warmup, mid=sampler.sample if rank == 0 else None)
     step_spread = dict(timed.step_ms)
+    if world > 1:                                                  # every rank's spread (which rank, which step was slow)
+        spreads = [None] * world
+        dist.all_gather_object(spreads, step_spread)
+        step_spread['per_rank'] = spreads
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / a.steps
     value = world * B * a.steps / (total_ms * 1e-3)
-    launches_per_step = pipe.launches_per_step()
+    launches_per_step = hmr.last_launches() if c4 else pipe.launches_per_step()
 
     # ---- e2e: public API with HOST (pinned) inputs; every step copies its inputs H2D and its results D2H inside the
     # timed region.  The copies ride on side streams (double-buffered staging) so they overlap the previous /
-    # next step's kernels -- what a serving loop built on the public API does.
+    # next step's kernels -- what a serving loop built on the public API does.  The CUDA graph is captured directly on the two
+    # staging sets (bind_inputs): no device-side copy of the inputs.
+    link = host_link_probe(dev)
     host = {k: v.cpu().pin_memory() for k, v in b.items()}
     keys = ('images', 'bbox_scale', 'bbox_center', 'img_w', 'img_h')
     staging = [{k: torch.empty_like(host[k], device=dev) for k in keys} for _ in range(2)]
@@ -291,6 +377,11 @@ def run_ours(a):
     host_rec = [torch.empty(B, RECORD_FLOATS, dtype=torch.float32).pin_memory() for _ in range(2)]
     s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     main = torch.cuda.current_stream(dev)
+    e2e_gather = None
+    if world > 1:
+        if gatherer is not None and hasattr(gatherer, 'close'):
+            gatherer.close()                                       # frees the value loop's receive regions before the e2e ones exist
+        e2e_gather, _ = sb.make_gatherer(B, dev)
 
     def e2e_run(steps):
         ev_h2d = [torch.cuda.Event() for _ in range(2)]
@@ -307,6 +398,16 @@ def run_ours(a):
                     staging[sl][k].copy_(host[k], non_blocking=True)
                 ev_h2d[sl].record(s_h2d)
 
+        def read_back(rec, sl):
+            rec_dev[sl].copy_(rec, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev)
+                host_rec[sl].copy_(rec_dev[sl], non_blocking=True)
+                ev_d2h[sl] = torch.cuda.Event()
+                ev_d2h[sl].record(s_d2h)
+
         with torch.cuda.stream(s_h2d):
             e0.record(s_h2d)
         issue_h2d(0)
@@ -317,18 +418,17 @@ def run_ours(a):
             main.wait_event(ev_h2d[sl])
             if ev_d2h[sl] is not None:
                 main.wait_event(ev_d2h[sl])                       # rec_dev[sl] read back by step i-2
-            st = staging[sl]
-            rec = pipe.forward_packed(st['images'], st['bbox_scale'], st['bbox_center'], st['img_w'], st['img_h'])
-            if world > 1:
-                rec = sb.all_gather_records(rec)[rank * B:(rank + 1) * B]
-            rec_dev[sl].copy_(rec, non_blocking=True)
+            rec = compute(staging[sl], bound=True)
             ev_used[sl] = torch.cuda.Event()
-            ev_used[sl].record(main)
-            with torch.cuda.stream(s_d2h):
-                s_d2h.wait_event(ev_used[sl])
-                host_rec[sl].copy_(rec_dev[sl], non_blocking=True)
-                ev_d2h[sl] = torch.cuda.Event()
-                ev_d2h[sl].record(s_d2h)
+            ev_used[sl].record(main)                               # inputs consumed (the record is complete): slot may be refilled
+            if world > 1:                                          # gather of step i overlaps step i+1; this rank reads back its own rows
+                prev = e2e_gather.submit(rec)
+                if prev is not None:
+                    read_back(prev[rank * B:(rank + 1) * B], (i - 1) % 2)
+            else:
+                read_back(rec, sl)
+        if world > 1:
+            read_back(e2e_gather.flush()[rank * B:(rank + 1) * B], (steps - 1) % 2)
         with torch.cuda.stream(s_d2h):
             e1.record(s_d2h)
         torch.cuda.synchronize(dev)
@@ -347,13 +447,20 @@ def run_ours(a):
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = host_rec[0].numel() * 4
+    link['h2d_floor_ms_per_step'] = round(h2d / (link['h2d_gbs'] * 1e9) * 1e3, 3)
+    link['d2h_floor_ms_per_step'] = round(d2h / (link['d2h_gbs'] * 1e9) * 1e3, 3)
+    if world > 1:
+        links = [None] * world
+        dist.all_gather_object(links, link)
+        link = {'per_rank': links}
 
     out = None
     if rank == 0:
         # ---- roofline: per-op CUDA-event timing of both trunks (live, eager, on the launching stream)
         peaks = load_peaks()
         conv_ms, conv_flops, step_ops_ms, conv_bytes = 0.0, 0.0, 0.0, 0
-        for m in (cc, hmr):
+        trunks = (hmr,) if c4 else (cc, hmr)
+        for m in trunks:
             m.backbone.profile_ops(b['images'])                   # warm
             rows = m.backbone.profile_ops(b['images'])
             conv_ms += sum(r['ms'] for r in rows if r['flops'] > 0)
@@ -361,47 +468,49 @@ def run_ours(a):
             conv_bytes += sum(r.get('bytes', 0) for r in rows if r['flops'] > 0)
             step_ops_ms += sum(r['ms'] for r in rows)
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
-        n_conv = sum(1 for m in (cc, hmr) for o in m.backbone._program.ops if o['type'] == 1)
+        n_conv = sum(1 for m in trunks for o in m.backbone._program.ops if o['type'] == 1)
+        traffic, traffic_src = (None, None) if c4 else load_ncu_traffic(a.backbone, B, a.precision)
         # ---- cpu baseline (bounded sample, rank 0, N=1 only)
         cpu = None
-        if world == 1 and not a.no_cpu_baseline:
-            if numa.get('bound'):                                  # the CPU baseline may use every host core again:
-                for tid in os.listdir('/proc/self/task'):          # reset every thread (OpenMP workers inherited the mask)
-                    try:
-                        os.sched_setaffinity(int(tid), numa['previous'])
-                    except OSError:
-                        pass
+        if world == 1 and not a.no_cpu_baseline and not c4:
+            sb.unbind_process(numa)                                # the CPU baseline may use every host core again
             ips, _, cores = time_oracle(a.backbone, a.cpu_sample, 2, 1)
             cpu = {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                    'sample': f'{a.cpu_sample}-image batches x2 of the same workload, fp32 PyTorch oracle (oracle/), {cores} threads'}
+        workload = (f'HMR forward with dataset-supplied camera (SPEC-SYN eval loop shape, trainer.py:235-245: int64 orig_shape, pre-computed R/K), '
+                    f'{a.backbone} -> HMR head -> SMPL -> projection, 224x224, batch {B}/GPU, random weights') if c4 else \
+                   f'SPEC full forward (CamCalib resnet50 -> (R,K) -> HMR {a.backbone} -> SMPL -> projection), 224x224, batch {B}/GPU, random weights'
         out = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'metric': METRIC if not c4 else 'images/sec HMR fwd with dataset cameras (224^2, b128)', 'value': value, 'unit': UNIT, 'n_gpus': world,
+            'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms_per_step, 'step_ms_spread': step_spread, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': a.precision, 'data': 'synthetic',
-            'config': {'workload': f'SPEC full forward (CamCalib resnet50 -> (R,K) -> HMR {a.backbone} -> SMPL -> projection), 224x224, batch {B}/GPU, random weights',
-                       'backbone': a.backbone, 'batch_per_gpu': B, 'global_batch': B * world, 'cuda_graph': not a.no_graph,
+            'config': {'workload': workload,
+                       'backbone': a.backbone, 'batch_per_gpu': B, 'global_batch': B * world, 'cuda_graph': not a.no_graph and not c4,
                        'numa': {k: v for k, v in numa.items() if k != 'previous'},
-                       'l2': 'inputs 154 MB/step/GPU > 126 MB L2, no explicit flush (weights stay L2-resident as in steady-state serving)',
-                       'parallelism': f'dp{world} (batch shard + one all-gather of 85,176 B/image records)' if world > 1 else 'single GPU'},
+                       'l2': f'inputs {B * 602112 / 1e6:.0f} MB/step/GPU > 126 MB L2, no explicit flush (weights stay L2-resident as in steady-state serving)',
+                       'parallelism': f'dp{world} (batch shard + one all-gather of 85,176 B/image records)' if world > 1 else 'single GPU',
+                       'gather': gather_desc},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / e2e_steps,
-                    'steps': e2e_steps, 'how': 'pinned host inputs -> H2D -> SPECPipeline.forward_packed -> D2H of the packed records; copies on side streams, double-buffered'},
+                    'steps': e2e_steps, 'host_link': link,
+                    'how': 'pinned host inputs -> H2D (double-buffered staging, graph captured on the staging buffers) -> forward -> D2H of the packed records; copies on side streams'},
             'gpu_launches': int(launches_per_step * a.steps),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
                          'frac': achieved / peaks['tf_sustained'],
-                         # dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step (2 trunks), from the
-                         # committed ncu --set full capture profiles/ncu_r01d.md (14.75 GB per trunk; resnet50, B=256, bf16)
-                         'traffic': 29.5e9 if (a.backbone == 'resnet50' and B == 256 and a.precision == 'bf16') else None,
+                         'traffic': traffic, 'traffic_source': traffic_src,
                          'algorithmic_bytes': conv_bytes,
-                         'kernel': 'tcgen05 implicit-GEMM conv family: conv_tcp/conv_tcp2 (cta_group::2)/conv_tc/conv3x3_halo/conv_stem7, %d launches/step' % n_conv,
-                         'how': 'sum of conv FLOPs of both trunks / sum of per-launch CUDA-event times (specb200_trunk_profile, eager, same stream)',
+                         'kernel': 'tcgen05 implicit-GEMM conv family (conv_tcp / conv_tcp2 cta_group::2 / conv_tc / conv3x3_halo / bottleneck / conv_stem7), %d conv ops/step' % n_conv,
+                         'how': 'sum of conv FLOPs of the trunks / sum of per-launch CUDA-event times (specb200_trunk_profile, eager, same stream)',
                          'peak_source': peaks['source'] + ' bf16 sustained', 'conv_ms_per_step': conv_ms,
                          'conv_share_of_trunk_ops': conv_ms / step_ops_ms if step_ops_ms else None,
-                         'step_frac_of_peak': (world * 0 + conv_flops) / (ms_per_step * 1e-3) / 1e12 / peaks['tf_sustained']},
+                         'step_frac_of_peak': conv_flops / (ms_per_step * 1e-3) / 1e12 / peaks['tf_sustained']},
             'cpu_baseline': cpu,
         }
         _emit(out)
     if world > 1:
+        if e2e_gather is not None and hasattr(e2e_gather, 'close'):
+            e2e_gather.close()
         dist.barrier()
         dist.destroy_process_group()
     return out
@@ -438,7 +547,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
+    ap.add_argument('--batch', type=int, default=0, help='images per GPU per step (default 256; 128 with --mode c4)')
+    ap.add_argument('--mode', default='spec', choices=['spec', 'c4'], help="spec: CamCalib -> HMR (BASELINE configs 2,3,5); c4: HMR with dataset cameras (config 4)")
     ap.add_argument('--backbone', default='resnet50')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32'])
     ap.add_argument('--chunk', type=int, default=int(os.environ.get('SPECB200_CHUNK', '0')))

@@ -82,6 +82,12 @@ int64_t specb200_trunk_workspace_bytes(specb200_trunk_t* t, int32_t batch, int32
 int specb200_trunk_forward(specb200_trunk_t* t, const float* images_nchw_dev, int32_t batch, int32_t h, int32_t w,
                            void* workspace_dev, int64_t workspace_bytes, float* pooled_out_dev, int32_t pooled_ld,
                            float* feat_nchw_out_dev, void* stream);
+/* Diagnostic: runs ops 0..stop_op of the program and writes the destination buffer of op stop_op -- the activation as the
+ * NEXT op would read it -- as fp32 NCHW [batch][*c_out][*h_out][*w_out] to act_out_dev (NULL: only report the shape).
+ * Lets a test compare every intermediate tensor with the oracle's (tests/test_gpu_parity.py::test_hrnet_layerwise_lowp). */
+int specb200_trunk_forward_until(specb200_trunk_t* t, const float* images_nchw_dev, int32_t batch, int32_t h, int32_t w,
+                                 void* workspace_dev, int64_t workspace_bytes, int32_t stop_op, int32_t* c_out, int32_t* h_out,
+                                 int32_t* w_out, float* act_out_dev, void* stream);
 /* number of kernels the last forward enqueued (bench.py's gpu_launches) */
 int64_t specb200_trunk_last_launches(specb200_trunk_t* t);
 int32_t specb200_trunk_num_ops(specb200_trunk_t* t);
@@ -207,6 +213,32 @@ int specb200_preproc_resize(specb200_preproc_t* t, const uint8_t* image_dev, int
                             int64_t row_stride_bytes, int32_t bgr, int32_t out_h, int32_t out_w, void* workspace_dev,
                             int64_t workspace_bytes, float* out_dev, uint8_t* raw_dev, void* stream);
 void specb200_preproc_destroy(specb200_preproc_t* t);
+
+/* ---- multi-GPU: all-gather of the packed per-image output records over NVLink peer memory.
+ *      The reference has no collective (one process, /root/reference/spec/tester.py:143-167); BASELINE.json's multi-GPU
+ *      configs shard the batch over one process per GPU and gather the records.  Each rank owns a receive region
+ *      (slots x world x block_bytes) that every peer maps through CUDA IPC; a gather is a PUT of this rank's block into all
+ *      peers' regions followed by a sequence-number flag exchange, all enqueued on the caller's stream (no host sync). ---- */
+typedef struct specb200_gather specb200_gather_t;
+#define SPECB200_IPC_HANDLE_BYTES 64
+#define SPECB200_GATHER_COPY_ENGINE 0 /* world-1 peer cudaMemcpyAsync (copy engines; SM-free) + 1-CTA signal / wait kernels */
+#define SPECB200_GATHER_PUSH_KERNEL 1 /* one kernel stores the block to every peer (16-byte stores) and signals           */
+/* Allocates this rank's receive region on the current device and writes its CUDA IPC handle (64 bytes) to
+ * ipc_handle_out_host.  block_bytes (multiple of 16) = bytes each rank contributes per gather. */
+int specb200_gather_create(specb200_gather_t** out, int32_t rank, int32_t world, int64_t block_bytes, int32_t slots,
+                           uint8_t* ipc_handle_out_host);
+/* all_handles_host: world x 64 bytes, the handles of all ranks in rank order (exchanged by the caller out of band --
+ * spec_b200 uses torch.distributed.all_gather_object); maps every peer's region (needs NVLink / PCIe peer access). */
+int specb200_gather_connect(specb200_gather_t* g, const uint8_t* all_handles_host);
+/* device pointer of receive slot `slot`: world x block_bytes, rank-major (= image order under a contiguous batch split) */
+void* specb200_gather_recv_ptr(specb200_gather_t* g, int32_t slot);
+/* Enqueues on `stream`: src_dev (block_bytes) -> slot `slot` of EVERY rank's region at this rank's offset; publishes `seq`
+ * (must grow by one per use of a slot) to all peers; waits until all peers published it.  When the stream reaches the end
+ * of this call's work, recv_ptr(slot) holds the blocks of all ranks.  A slot may be reused once every rank has enqueued
+ * its consumers of the previous content before its own next call (three slots make that automatic for a pipelined loop). */
+int specb200_allgather_outputs(specb200_gather_t* g, const void* src_dev, int32_t slot, uint32_t seq, int32_t mode, void* stream);
+int specb200_gather_set_push_ctas(specb200_gather_t* g, int32_t ctas);
+void specb200_gather_destroy(specb200_gather_t* g);
 
 /* ---- standalone ops (unit tests / building blocks) -------------------------------------------- */
 /* out[m][n] = sum_k a[m][k] w[n][k] + bias[n] ; fp32 */

@@ -56,6 +56,8 @@ _PROTOS = {
     'specb200_trunk_workspace_bytes': (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     'specb200_trunk_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    'specb200_trunk_forward_until': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                               _I, _I, _I, C.c_void_p, C.c_void_p]),
     'specb200_trunk_last_launches': (C.c_int64, [C.c_void_p]),
     'specb200_trunk_num_ops': (C.c_int32, [C.c_void_p]),
     'specb200_trunk_profile': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
@@ -92,6 +94,12 @@ _PROTOS = {
     'specb200_preproc_resize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'specb200_preproc_destroy': (None, [C.c_void_p]),
+    'specb200_gather_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    'specb200_gather_connect': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'specb200_gather_recv_ptr': (C.c_void_p, [C.c_void_p, C.c_int32]),
+    'specb200_allgather_outputs': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]),
+    'specb200_gather_set_push_ctas': (C.c_int, [C.c_void_p, C.c_int32]),
+    'specb200_gather_destroy': (None, [C.c_void_p]),
     'specb200_linear_f32': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
@@ -132,3 +140,26 @@ def require_device(t=None):
     if not torch.cuda.is_available():
         raise RuntimeError('spec_b200 has no CPU path: no CUDA device available')
     check(lib().specb200_device_check())
+
+
+def refuse_training(module):
+    """The library implements the INFERENCE path only (eval-mode BatchNorm folded into the conv weights, dropout = identity,
+    no autograd graph).  The reference shares these classes with its trainer (spec/trainer.py:50-56): a ``forward`` in training
+    mode with gradients enabled would silently train nothing, so it raises instead."""
+    import torch
+    if module.training and torch.is_grad_enabled():
+        raise RuntimeError(f'{type(module).__name__}: spec_b200 implements the inference path only -- call .eval() and/or run under '
+                           'torch.no_grad(); training (spec/trainer.py) is out of scope')
+
+
+class VersionWatch:
+    """In-place version counters of every parameter and buffer of some modules, snapshotted when their packed device copies
+    are made: lets the next forward notice in-place updates (optimizer steps, ``param.data.copy_``) that neither
+    ``load_state_dict`` nor ``_apply`` report.  Checking costs one attribute read per tensor (~50 us for two ResNet-50s)."""
+
+    def __init__(self, *modules):
+        self.tensors = [t for m in modules for t in list(m.parameters()) + list(m.buffers())]
+        self.snap = tuple(t._version for t in self.tensors)
+
+    def changed(self):
+        return tuple(t._version for t in self.tensors) != self.snap

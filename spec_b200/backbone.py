@@ -298,10 +298,14 @@ class Trunk(nn.Module):
         return 2 * macs
 
     # ---- engine
+    def _weights_changed(self):
+        w = getattr(self, '_watch', None)
+        return w is None or w.changed()
+
     def _ensure(self, device):
         key = (device, self.precision)
         L = _lib.lib()
-        if self._handle is not None and key == self._handle_key and not self._dirty:
+        if self._handle is not None and key == self._handle_key and not self._dirty and not self._weights_changed():
             return
         _lib.require_device()
         self._release()
@@ -324,15 +328,17 @@ class Trunk(nn.Module):
             self._handle = h
             self._handle_key = key
             _lib.check(L.specb200_trunk_set_chunk(h, self.chunk))
-            mods = dict(self.named_modules())
+            # BatchNorm is folded ON THE HOST in fp64 (one D2H copy of the whole state_dict, then CPU arithmetic): no torch
+            # kernels are launched on the device for it -- the only device work of a forward is libspecb200's own kernels
+            host = {k: v.detach().cpu() for k, v in self.state_dict().items()}
             for slot, (cp, bp, cout, cin, k) in enumerate(P.convs):
-                conv, bn = mods[cp], mods[bp]
-                w = conv.weight.detach().double()
-                scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
-                wf = (w * scale.view(-1, 1, 1, 1)).float().contiguous().cpu()
-                bf = (bn.bias.detach().double() - bn.running_mean.detach().double() * scale).float().contiguous().cpu()
+                w = host[cp + '.weight'].double()
+                scale = host[bp + '.weight'].double() / torch.sqrt(host[bp + '.running_var'].double() + _BN_EPS)
+                wf = (w * scale.view(-1, 1, 1, 1)).float().contiguous()
+                bf = (host[bp + '.bias'].double() - host[bp + '.running_mean'].double() * scale).float().contiguous()
                 _lib.check(L.specb200_trunk_set_conv(h, slot, wf.data_ptr(), bf.data_ptr(), cout, wf.shape[1], k, k))
         self._dirty = False
+        self._watch = _lib.VersionWatch(self)
 
     def out_shape(self, h, w):
         c, ho, wo = C.c_int32(), C.c_int32(), C.c_int32()
@@ -354,6 +360,7 @@ class Trunk(nn.Module):
         """Enqueue the trunk on the current stream.  ``pooled``: fp32 tensor (or raw pointer) receiving the
         global-average-pooled feature per image with row stride ``pooled_ld`` floats."""
         _lib.require_device(images)
+        _lib.refuse_training(self)
         if images.dim() != 4 or images.shape[1] != 3 or not images.is_floating_point():
             raise ValueError('images must be a floating-point (B,3,H,W) tensor')
         if images.shape[0] == 0:
@@ -373,6 +380,25 @@ class Trunk(nn.Module):
                 self._handle, images.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), pptr, pooled_ld,
                 feat.data_ptr() if feat is not None else 0, stream))
         return feat
+
+    def activation_after(self, images, op_index):
+        """Diagnostic: the fp32 NCHW activation in the destination buffer of program op ``op_index`` right after it ran
+        (``specb200_trunk_forward_until``) -- for conv ops that is conv + folded BN (+ residual) (+ ReLU) as stored."""
+        _lib.require_device(images)
+        images = images.float().contiguous()
+        B, _, H, W = images.shape
+        self._ensure(images.device)
+        ws = self._workspace(B, H, W, images.device)
+        c, ho, wo = C.c_int32(), C.c_int32(), C.c_int32()
+        L = _lib.lib()
+        stream = torch.cuda.current_stream(images.device).cuda_stream
+        with torch.cuda.device(images.device):
+            _lib.check(L.specb200_trunk_forward_until(self._handle, images.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), op_index,
+                                                      C.byref(c), C.byref(ho), C.byref(wo), None, stream))
+            out = torch.empty(B, c.value, ho.value, wo.value, dtype=torch.float32, device=images.device)
+            _lib.check(L.specb200_trunk_forward_until(self._handle, images.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), op_index,
+                                                      C.byref(c), C.byref(ho), C.byref(wo), out.data_ptr(), stream))
+        return out
 
     def last_launches(self):
         return int(_lib.lib().specb200_trunk_last_launches(self._handle)) if self._handle else 0

@@ -37,6 +37,7 @@ class CameraRegressorNetwork(nn.Module):
             self.fc_roll = self._get_fc_layers(num_fc_layers, num_fc_channels, out_channels)
         self._handle = None
         self._dirty = True
+        self._watch = None
         self._ws = None
         self.register_load_state_dict_post_hook(lambda m, k: m._mark_dirty())
 
@@ -70,7 +71,8 @@ class CameraRegressorNetwork(nn.Module):
             pass
 
     def _ensure(self, device):
-        if self._handle is not None and not self._dirty and self._device == device:
+        heads = (self.fc_vfov, self.fc_pitch, self.fc_roll)
+        if self._handle is not None and not self._dirty and self._device == device and not self._watch.changed():
             return
         _lib.require_device()
         self._release()
@@ -87,10 +89,12 @@ class CameraRegressorNetwork(nn.Module):
             _lib.check(L.specb200_camtail_finalize(h))
         self._device = device
         self._dirty = False
+        self._watch = _lib.VersionWatch(*heads)
 
     def logits(self, images):
         """(B, 3*num_out) fp32 logits [vfov|pitch|roll]."""
         _lib.require_device(images)
+        _lib.refuse_training(self)
         dev = images.device
         self._ensure(dev)
         B = images.shape[0]

@@ -10,11 +10,16 @@
 #include <vector>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/specb200.h"
 #include "internal.h"
 #include "tail.h"
 
 namespace sb {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -38,6 +43,7 @@ struct specb200_trunk {
     std::vector<specb200_op_t> ops;
     std::vector<int> buf_ch;
     std::vector<ConvWeights> w;
+    std::vector<ConvWeights> w_plain;       // pair slots only: the plain [32][32][3][3] packing for odd widths
     std::vector<int> wslot_cin;      // stored (padded) Cin of the op using the slot
     std::vector<int> wslot_pair;     // slot belongs to a pixel-pair conv (weights expanded to 64 x 64)
     int out_buf = 0;
@@ -123,6 +129,7 @@ extern "C" int specb200_trunk_create(specb200_trunk_t** out, const specb200_op_t
     t->ops.assign(ops, ops + n_ops);
     t->buf_ch.assign(buf_channels, buf_channels + n_bufs);
     t->w.resize(n_wslots);
+    t->w_plain.resize(n_wslots);
     t->wslot_cin.assign(n_wslots, 0);
     t->wslot_pair.assign(n_wslots, 0);
     t->out_buf = out_buf;
@@ -157,41 +164,21 @@ static void free_weights(ConvWeights& w) {
     w = ConvWeights();
 }
 
-extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const float* w_host, const float* b_host,
-                                       int32_t cout, int32_t cin, int32_t kh, int32_t kw) {
-    if (!t || wslot < 0 || wslot >= static_cast<int>(t->w.size()) || !w_host || !b_host) { set_error("set_conv: bad arguments"); return 1; }
-    std::vector<float> pair_w, pair_b;
-    int cin_s = t->wslot_cin[wslot];                 // stored Cin (>= cin, zero padded)
-    if (t->wslot_pair[wslot]) {
-        // Pixel-pair view: [H][W][32] == [H][W/2][64].  Output pixel x = 2X + po reads input x + dx = 2(X + s) + pi with
-        // s = floor((po + dx) / 2), pi = (po + dx) mod 2, so the 32->32 3x3 conv is a 64->64 3x3 conv on the half-width
-        // grid whose weights are W2[po*32+co][pi*32+ci][kh][s+1] = w[co][ci][kh][dx+1] (half of them structurally zero).
-        if (cin != 32 || cout != 32 || kh != 3 || kw != 3) { set_error("set_conv: pair slot expects [32][32][3][3]"); return 1; }
-        pair_w.assign(static_cast<size_t>(64) * 64 * 9, 0.f);
-        pair_b.resize(64);
-        for (int po = 0; po < 2; ++po)
-            for (int co = 0; co < 32; ++co) {
-                pair_b[po * 32 + co] = b_host[co];
-                for (int ci = 0; ci < 32; ++ci)
-                    for (int y = 0; y < 3; ++y)
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const int q = po + dx;
-                            const int sft = (q < 0) ? -1 : (q >= 2 ? 1 : 0);
-                            const int pi = q - 2 * sft;
-                            pair_w[((static_cast<size_t>(po * 32 + co) * 64 + pi * 32 + ci) * 3 + y) * 3 + (sft + 1)] =
-                                w_host[((static_cast<size_t>(co) * 32 + ci) * 3 + y) * 3 + (dx + 1)];
-                        }
-            }
-        w_host = pair_w.data(); b_host = pair_b.data();
-        cout = 64; cin = 64; cin_s = 64;
-    }
-    if (cin_s < cin) { set_error("set_conv: weight cin exceeds the op's cin"); return 1; }
-    ConvWeights& w = t->w[wslot];
+// Packs one conv (BN already folded) into `w` for the precision / kernel family of the trunk.
+static bool pack_conv(specb200_trunk* t, ConvWeights& w, bool stem7, const float* w_host, const float* b_host, int cout, int cin, int cin_s,
+                      int kh, int kw) {
+    if (cin_s < cin) { set_error("set_conv: weight cin exceeds the op's cin"); return false; }
     free_weights(w);
     w.cout = cout; w.cin = cin_s; w.kh = kh; w.kw = kw;
     w.K = kh * kw * cin_s;
-    if (!check_cuda(cudaMalloc(&w.bias, sizeof(float) * cout), "cudaMalloc bias")) return 1;
-    if (!check_cuda(cudaMemcpy(w.bias, b_host, sizeof(float) * cout, cudaMemcpyHostToDevice), "bias upload")) return 1;
+    if (!check_cuda(cudaMalloc(&w.bias, sizeof(float) * cout), "cudaMalloc bias")) return false;
+    if (!check_cuda(cudaMemcpy(w.bias, b_host, sizeof(float) * cout, cudaMemcpyHostToDevice), "bias upload")) return false;
+    auto to16 = [&](float v) {
+        uint16_t bits;
+        if (t->prec == PREC_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(v); memcpy(&bits, &h, 2); }
+        else { __half h = __float2half_rn(v); memcpy(&bits, &h, 2); }
+        return bits;
+    };
     if (t->prec == PREC_F32) {
         std::vector<float> pk(static_cast<size_t>(w.K) * cout, 0.f);
         for (int o = 0; o < cout; ++o)
@@ -199,25 +186,20 @@ extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const
                 for (int y = 0; y < kh; ++y)
                     for (int x = 0; x < kw; ++x)
                         pk[(static_cast<size_t>(y * kw + x) * cin_s + c) * cout + o] = w_host[((static_cast<size_t>(o) * cin + c) * kh + y) * kw + x];
-        if (!check_cuda(cudaMalloc(&w.w_f32, pk.size() * sizeof(float)), "cudaMalloc w_f32")) return 1;
-        if (!check_cuda(cudaMemcpy(w.w_f32, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice), "w upload")) return 1;
-    } else if (wslot == t->stem7_slot) {
-        if (cin != 3 || cout != 64 || kh != 7 || kw != 7) { set_error("set_conv: stem weights must be [64][3][7][7]"); return 1; }
+        if (!check_cuda(cudaMalloc(&w.w_f32, pk.size() * sizeof(float)), "cudaMalloc w_f32")) return false;
+        if (!check_cuda(cudaMemcpy(w.w_f32, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice), "w upload")) return false;
+    } else if (stem7) {
+        if (cin != 3 || cout != 64 || kh != 7 || kw != 7) { set_error("set_conv: stem weights must be [64][3][7][7]"); return false; }
         w.stem7 = true; w.block_n = 64; w.cout_pad = 64; w.K = 168; w.K_pad = 192;
         std::vector<uint16_t> pk(static_cast<size_t>(64) * 192, 0);
         for (int o = 0; o < 64; ++o)
             for (int c = 0; c < 3; ++c)
                 for (int y = 0; y < 7; ++y)
-                    for (int x = 0; x < 7; ++x) {
-                        const float v = w_host[((static_cast<size_t>(o) * 3 + c) * 7 + y) * 7 + x];
-                        uint16_t bits;
-                        if (t->prec == PREC_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(v); memcpy(&bits, &h, 2); }
-                        else { __half h = __float2half_rn(v); memcpy(&bits, &h, 2); }
-                        pk[static_cast<size_t>(o) * 192 + (c * 7 + y) * 8 + x] = bits;
-                    }
-        if (!check_cuda(cudaMalloc(&w.w_tc, pk.size() * 2), "cudaMalloc w_tc")) return 1;
-        if (!check_cuda(cudaMemcpy(w.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice), "w upload")) return 1;
-        if (!conv_tc_make_weight_tmap(w)) return 1;
+                    for (int x = 0; x < 7; ++x)
+                        pk[static_cast<size_t>(o) * 192 + (c * 7 + y) * 8 + x] = to16(w_host[((static_cast<size_t>(o) * 3 + c) * 7 + y) * 7 + x]);
+        if (!check_cuda(cudaMalloc(&w.w_tc, pk.size() * 2), "cudaMalloc w_tc")) return false;
+        if (!check_cuda(cudaMemcpy(w.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice), "w upload")) return false;
+        if (!conv_tc_make_weight_tmap(w)) return false;
     } else {
         w.block_n = conv_tc_pick_block_n(cout, kh * kw * cin_s);
         if (cin_s == 4) {                           // stem layout: K index = (y*kwp + x)*4 + c
@@ -232,18 +214,44 @@ extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const
         for (int o = 0; o < cout; ++o)
             for (int c = 0; c < cin; ++c)
                 for (int y = 0; y < kh; ++y)
-                    for (int x = 0; x < kw; ++x) {
-                        const float v = w_host[((static_cast<size_t>(o) * cin + c) * kh + y) * kw + x];
-                        uint16_t bits;
-                        if (t->prec == PREC_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(v); memcpy(&bits, &h, 2); }
-                        else { __half h = __float2half_rn(v); memcpy(&bits, &h, 2); }
-                        pk[static_cast<size_t>(o) * w.K_pad + static_cast<size_t>(y * kw_eff + x) * cin_s + c] = bits;
-                    }
-        if (!check_cuda(cudaMalloc(&w.w_tc, pk.size() * 2), "cudaMalloc w_tc")) return 1;
-        if (!check_cuda(cudaMemcpy(w.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice), "w upload")) return 1;
-        if (!conv_tc_make_weight_tmap(w)) return 1;
+                    for (int x = 0; x < kw; ++x)
+                        pk[static_cast<size_t>(o) * w.K_pad + static_cast<size_t>(y * kw_eff + x) * cin_s + c] =
+                            to16(w_host[((static_cast<size_t>(o) * cin + c) * kh + y) * kw + x]);
+        if (!check_cuda(cudaMalloc(&w.w_tc, pk.size() * 2), "cudaMalloc w_tc")) return false;
+        if (!check_cuda(cudaMemcpy(w.w_tc, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice), "w upload")) return false;
+        if (!conv_tc_make_weight_tmap(w)) return false;
     }
-    return 0;
+    return true;
+}
+
+extern "C" int specb200_trunk_set_conv(specb200_trunk_t* t, int32_t wslot, const float* w_host, const float* b_host,
+                                       int32_t cout, int32_t cin, int32_t kh, int32_t kw) {
+    if (!t || wslot < 0 || wslot >= static_cast<int>(t->w.size()) || !w_host || !b_host) { set_error("set_conv: bad arguments"); return 1; }
+    const int cin_s = t->wslot_cin[wslot];           // stored Cin (>= cin, zero padded)
+    if (t->wslot_pair[wslot]) {
+        // Pixel-pair view: [H][W][32] == [H][W/2][64].  Output pixel x = 2X + po reads input x + dx = 2(X + s) + pi with
+        // s = floor((po + dx) / 2), pi = (po + dx) mod 2, so the 32->32 3x3 conv is a 64->64 3x3 conv on the half-width
+        // grid whose weights are W2[po*32+co][pi*32+ci][kh][s+1] = w[co][ci][kh][dx+1] (half of them structurally zero).
+        // The view needs an even width: the plain [32][32][3][3] packing is kept beside it for odd widths (gather kernel).
+        if (cin != 32 || cout != 32 || kh != 3 || kw != 3) { set_error("set_conv: pair slot expects [32][32][3][3]"); return 1; }
+        if (!pack_conv(t, t->w_plain[wslot], false, w_host, b_host, cout, cin, cin_s, kh, kw)) return 1;
+        std::vector<float> pair_w(static_cast<size_t>(64) * 64 * 9, 0.f), pair_b(64);
+        for (int po = 0; po < 2; ++po)
+            for (int co = 0; co < 32; ++co) {
+                pair_b[po * 32 + co] = b_host[co];
+                for (int ci = 0; ci < 32; ++ci)
+                    for (int y = 0; y < 3; ++y)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int q = po + dx;
+                            const int sft = (q < 0) ? -1 : (q >= 2 ? 1 : 0);
+                            const int pi = q - 2 * sft;
+                            pair_w[((static_cast<size_t>(po * 32 + co) * 64 + pi * 32 + ci) * 3 + y) * 3 + (sft + 1)] =
+                                w_host[((static_cast<size_t>(co) * 32 + ci) * 3 + y) * 3 + (dx + 1)];
+                        }
+            }
+        return pack_conv(t, t->w[wslot], false, pair_w.data(), pair_b.data(), 64, 64, 64, 3, 3) ? 0 : 1;
+    }
+    return pack_conv(t, t->w[wslot], t->prec != PREC_F32 && wslot == t->stem7_slot, w_host, b_host, cout, cin, cin_s, kh, kw) ? 0 : 1;
 }
 
 extern "C" int specb200_trunk_set_chunk(specb200_trunk_t* t, int32_t chunk) {
@@ -272,10 +280,11 @@ extern "C" int64_t specb200_trunk_workspace_bytes(specb200_trunk_t* t, int32_t b
     return static_cast<int64_t>(total + 1024);
 }
 
-extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, int32_t batch, int32_t h, int32_t w,
-                                      void* workspace, int64_t workspace_bytes, float* pooled_out, int32_t pooled_ld,
-                                      float* feat_out, void* stream) {
+static int trunk_forward_impl(specb200_trunk_t* t, const float* images, int32_t batch, int32_t h, int32_t w,
+                              void* workspace, int64_t workspace_bytes, float* pooled_out, int32_t pooled_ld,
+                              float* feat_out, void* stream, int stop_op) {
     if (!t || !images || !workspace || batch <= 0) { set_error("trunk_forward: bad arguments"); return 1; }
+    NvtxRange nvtx_trunk("specb200:trunk (backbone convs + pool)");
     if (!trunk_plan(t, h, w)) return 1;
     if (workspace_bytes < specb200_trunk_workspace_bytes(t, batch, h, w)) { set_error("trunk_forward: workspace too small"); return 1; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -307,15 +316,16 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
                 if (!conv_stem7_launch(images + static_cast<size_t>(b0) * 3 * h * w, buf[o.dst], cw, nb, sS.H, sS.W, dS.H, dS.W, t->prec, s)) return 1;
                 ++launches;
                 mark();
+                if (stop_op == 0) break;
                 continue;
             }
             switch (o.type) {
                 case SPECB200_OP_CONV: {
-                    const ConvWeights& cw = t->w[o.wslot];
+                    // the pixel-pair view needs an even width; odd widths take the plain packing (gather kernel)
+                    const bool pair = t->wslot_pair[o.wslot] != 0 && !((sS.W & 1) || (dS.W & 1));
+                    const ConvWeights& cw = (t->wslot_pair[o.wslot] != 0 && !pair) ? t->w_plain[o.wslot] : t->w[o.wslot];
                     if (cw.bias == nullptr) { set_error("trunk_forward: conv weights for slot " + std::to_string(o.wslot) + " not set"); return 1; }
-                    const bool pair = t->wslot_pair[o.wslot] != 0;
                     if (cw.cout != (pair ? 64 : o.cout) || cw.kh != o.kh || cw.kw != o.kw) { set_error("trunk_forward: weight shape mismatch at op " + std::to_string(i)); return 1; }
-                    if (pair && ((sS.W & 1) || (dS.W & 1))) { set_error("trunk_forward: pixel-pair conv needs an even width (op " + std::to_string(i) + ")"); return 1; }
                     ConvParams p;
                     p.in = buf[o.src]; p.out = buf[o.dst]; p.res = o.src2 >= 0 ? buf[o.src2] : nullptr; p.bias = cw.bias;
                     p.N = nb; p.H = sS.H; p.W = sS.W; p.Cin = o.cin; p.Ho = dS.H; p.Wo = dS.W; p.Cout = o.cout;
@@ -352,6 +362,13 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
             }
             ++launches;
             mark();
+            if (static_cast<int>(i) == stop_op) break;
+        }
+        if (stop_op >= 0) {                                   // debug read-out of an intermediate activation (whole batch at once)
+            const specb200_op_t& o = t->ops[stop_op];
+            const BufShape dS = t->op_dst[stop_op];
+            if (!nhwc_to_nchw_f32_launch(buf[o.dst], feat_out, nb, dS.H, dS.W, t->buf_ch[o.dst], t->prec, s)) return 1;
+            break;
         }
         if (pooled_out) {
             if (!avgpool_launch(buf[t->out_buf], pooled_out + static_cast<size_t>(b0) * pooled_ld, pooled_ld, nb, t->out_h * t->out_w, C_out, t->prec, s)) return 1;
@@ -365,6 +382,25 @@ extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, 
     }
     t->last_launches = launches;
     return 0;
+}
+
+extern "C" int specb200_trunk_forward(specb200_trunk_t* t, const float* images, int32_t batch, int32_t h, int32_t w,
+                                      void* workspace, int64_t workspace_bytes, float* pooled_out, int32_t pooled_ld,
+                                      float* feat_out, void* stream) {
+    return trunk_forward_impl(t, images, batch, h, w, workspace, workspace_bytes, pooled_out, pooled_ld, feat_out, stream, -1);
+}
+
+extern "C" int specb200_trunk_forward_until(specb200_trunk_t* t, const float* images, int32_t batch, int32_t h, int32_t w,
+                                            void* workspace, int64_t workspace_bytes, int32_t stop_op, int32_t* c_out, int32_t* h_out,
+                                            int32_t* w_out, float* act_out, void* stream) {
+    if (!t || stop_op < 0 || stop_op >= static_cast<int>(t->ops.size())) { set_error("trunk_forward_until: bad op index"); return 1; }
+    if (!trunk_plan(t, h, w)) return 1;
+    if (t->chunk > 0 && t->chunk < batch) { set_error("trunk_forward_until: not with batch chunking"); return 1; }
+    if (c_out) *c_out = t->buf_ch[t->ops[stop_op].dst];
+    if (h_out) *h_out = t->op_dst[stop_op].H;
+    if (w_out) *w_out = t->op_dst[stop_op].W;
+    if (!act_out) return 0;                                   // shape query only
+    return trunk_forward_impl(t, images, batch, h, w, workspace, workspace_bytes, nullptr, 0, act_out, stream, stop_op);
 }
 
 extern "C" int64_t specb200_trunk_last_launches(specb200_trunk_t* t) { return t ? t->last_launches : 0; }
@@ -401,6 +437,7 @@ extern "C" int specb200_trunk_profile(specb200_trunk_t* t, const float* images, 
 extern "C" void specb200_trunk_destroy(specb200_trunk_t* t) {
     if (!t) return;
     for (auto& w : t->w) free_weights(w);
+    for (auto& w : t->w_plain) free_weights(w);
     delete t;
 }
 
@@ -463,6 +500,7 @@ extern "C" int64_t specb200_camtail_workspace_bytes(specb200_camtail_t* t, int32
 extern "C" int specb200_camtail_forward(specb200_camtail_t* t, const float* pooled, int32_t pooled_ld, int32_t batch,
                                         void* workspace, int64_t workspace_bytes, float* logits_out, void* stream) {
     if (!t || !pooled || !logits_out || batch <= 0) { set_error("camtail_forward: bad arguments"); return 1; }
+    NvtxRange nvtx_cam("specb200:camcalib_fc");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int ldo = 3 * t->num_out;
     if (t->fused)
@@ -489,6 +527,7 @@ extern "C" int specb200_camcalib_decode(const float* logits, int32_t logits_ld, 
                                         const float* img_h, const float* img_w, float* angles_out, float* rotmat_out,
                                         float* intr_out, float* fpix_out, void* stream) {
     if (!logits || !angles_out || batch <= 0) { set_error("camcalib_decode: bad arguments"); return 1; }
+    NvtxRange nvtx_dec("specb200:camcalib_decode (softargmax, f_pix, R, K)");
     if (rotmat_out && (!img_h || !img_w || !intr_out)) { set_error("camcalib_decode: img_h/img_w/intrinsics required with rotmat"); return 1; }
     return camcalib_decode_launch(logits, logits_ld, num_out, img_h, img_w, angles_out, rotmat_out, intr_out, fpix_out, batch,
                                   static_cast<cudaStream_t>(stream)) ? 0 : 1;
@@ -648,6 +687,7 @@ extern "C" int specb200_hmrtail_forward(specb200_hmrtail_t* t, int32_t B, void* 
         set_error("hmrtail_forward: null output pointer"); return 1;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NvtxRange nvtx_tail("specb200:hmr_tail (head x3, rot6d, SMPL LBS, joints, projection)");
     const HmrWs w = hmr_carve(t, B, workspace);
     const int C = t->C, ldx = t->ldx;
     int64_t n = 0;

@@ -41,6 +41,13 @@ struct ConvWeights {
 
 void set_error(const std::string& msg);
 
+// NVTX range per stage of the path: visible in nsys / ncu --nvtx timelines, a no-op (one
+// predictable branch in the header-only NVTX3 stub) when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+
 // cudaFuncSetAttribute is per DEVICE: remember per (function instantiation, device) whether the opt-in was done.
 struct DeviceOnce {
     bool done[64] = {};

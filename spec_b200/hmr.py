@@ -29,21 +29,53 @@ SMPL_MEAN_PARAMS = os.environ.get('SPECB200_SMPL_MEAN_PARAMS', 'data/smpl_mean_p
 JOINT_REGRESSOR_TRAIN_EXTRA = os.environ.get('SPECB200_J_REGRESSOR_EXTRA', 'data/J_regressor_extra.npy')
 
 
+def synthetic_assets_allowed():
+    """Seeded synthetic SMPL constants / mean parameters stand in for the licensed assets ONLY on an explicit opt-in
+    (``SPECB200_SYNTHETIC_ASSETS=1``: tests, bench, smoke -- there is no network to fetch the real files) or when the caller
+    passes ``smpl_data=`` / ``mean_params=`` itself.  Otherwise a missing file raises, as the reference does
+    (smplx raises on a missing model file; pare's HMRHead np.load()s SMPL_MEAN_PARAMS unconditionally)."""
+    return os.environ.get('SPECB200_SYNTHETIC_ASSETS', '0') == '1'
+
+
+def _dense(a):
+    return np.asarray(a.toarray() if hasattr(a, 'toarray') else a)
+
+
+def _read_smpl_file(path):
+    """An ``.npz`` export or the ``SMPL_NEUTRAL.pkl`` smplx loads (a latin-1 pickle of arrays; the original chumpy-typed
+    release needs ``chumpy`` importable or a one-off export: ``np.savez(npz, **{k: np.array(v) for k, v in pkl.items()})``)."""
+    if path.endswith('.npz'):
+        return dict(np.load(path, allow_pickle=False))
+    import pickle
+    try:
+        with open(path, 'rb') as fh:
+            return dict(pickle.load(fh, encoding='latin1'))
+    except ModuleNotFoundError as e:                        # chumpy-typed original release
+        raise RuntimeError(f'{path} needs the {e.name!r} package to unpickle; export it to SMPL_NEUTRAL.npz once '
+                           '(see spec_b200/hmr.py::_read_smpl_file)') from e
+
+
 def _load_smpl_data():
-    """SMPL constants from an .npz export under SMPL_MODEL_DIR if present, else seeded synthetic ones."""
-    npz = os.path.join(SMPL_MODEL_DIR, 'SMPL_NEUTRAL.npz')
-    if os.path.exists(npz) and os.path.exists(JOINT_REGRESSOR_TRAIN_EXTRA):
-        d = dict(np.load(npz))
-        out = {k: np.asarray(d[k], dtype=np.float32) for k in ('v_template', 'shapedirs', 'J_regressor')}
+    """SMPL constants from ``SMPL_NEUTRAL.npz`` / ``SMPL_NEUTRAL.pkl`` under SMPL_MODEL_DIR (spec/config.py:35) plus
+    ``J_regressor_extra.npy`` (config.py:36)."""
+    cands = [os.path.join(SMPL_MODEL_DIR, n) for n in ('SMPL_NEUTRAL.npz', 'SMPL_NEUTRAL.pkl')]
+    path = next((c for c in cands if os.path.exists(c)), None)
+    if path is not None and os.path.exists(JOINT_REGRESSOR_TRAIN_EXTRA):
+        d = _read_smpl_file(path)
+        out = {k: _dense(d[k]).astype(np.float32) for k in ('v_template', 'shapedirs', 'J_regressor')}
         out['shapedirs'] = out['shapedirs'][:, :, :10]
-        pd = np.asarray(d['posedirs'], dtype=np.float32)
+        pd = _dense(d['posedirs']).astype(np.float32)
         out['posedirs'] = pd.reshape(-1, pd.shape[-1]).T if pd.ndim == 3 else pd
-        out['lbs_weights'] = np.asarray(d['weights'] if 'weights' in d else d['lbs_weights'], dtype=np.float32)
+        out['lbs_weights'] = _dense(d['weights'] if 'weights' in d else d['lbs_weights']).astype(np.float32)
         out['J_regressor_extra'] = np.load(JOINT_REGRESSOR_TRAIN_EXTRA).astype(np.float32)
         out['parents'] = np.asarray(SMPL_PARENTS, dtype=np.int64)
         return out
+    if not synthetic_assets_allowed():
+        raise FileNotFoundError(
+            f'SMPL model not found: looked for {cands} and {JOINT_REGRESSOR_TRAIN_EXTRA!r} (set SPECB200_SMPL_DIR / '
+            'SPECB200_J_REGRESSOR_EXTRA, pass smpl_data=, or opt in to seeded synthetic constants with SPECB200_SYNTHETIC_ASSETS=1)')
     warnings.warn(f'SMPL model not found under {SMPL_MODEL_DIR!r}: using seeded SYNTHETIC SMPL constants '
-                  '(right shapes, meaningless geometry)', stacklevel=3)
+                  '(right shapes, meaningless geometry; SPECB200_SYNTHETIC_ASSETS=1)', stacklevel=3)
     return synthetic_smpl_data(0)
 
 
@@ -52,6 +84,10 @@ def _load_mean_params():
         d = np.load(SMPL_MEAN_PARAMS)
         return {'pose': d['pose'].astype(np.float32), 'shape': d['shape'].astype(np.float32),
                 'cam': d['cam'].astype(np.float32)}
+    if not synthetic_assets_allowed():
+        raise FileNotFoundError(f'{SMPL_MEAN_PARAMS!r} not found (set SPECB200_SMPL_MEAN_PARAMS, pass mean_params=, or opt in to '
+                                'seeded synthetic values with SPECB200_SYNTHETIC_ASSETS=1)')
+    warnings.warn(f'{SMPL_MEAN_PARAMS!r} not found: using seeded SYNTHETIC mean parameters (SPECB200_SYNTHETIC_ASSETS=1)', stacklevel=3)
     return synthetic_mean_params(0)
 
 
@@ -155,13 +191,46 @@ class HMR(nn.Module):
             self.load_pretrained(pretrained)
 
     # ---- checkpoint helpers (hmr.py:124-135)
-    def load_pretrained(self, file):
+    def load_pretrained(self, file, strict_report=True):
+        """hmr.py:124-135: backbone and head are filled from ONE flat state_dict, non-strictly.  Non-strict loading hides
+        naming mismatches (the HRNet ``-conv`` tail is ``downsample_layers.{i}.*`` here; upstream pare is believed to call
+        it ``downsample_stage_{i+1}.*`` -- un-checkable offline, so both spellings are accepted), so every backbone / head
+        tensor that the checkpoint did NOT fill is reported: a RuntimeError with ``strict_report`` (default), else a warning."""
         sd = torch.load(file, map_location='cpu')
         sd = sd.get('model', sd.get('state_dict', sd))
         sd = {k[len('model.'):] if k.startswith('model.') else k: v for k, v in sd.items()}
-        self.backbone.load_state_dict({k: v for k, v in sd.items() if k in self.backbone.state_dict()}, strict=False)
-        own = self.head.state_dict()
-        self.head.load_state_dict({k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}, strict=False)
+        missing = self.load_flat_state_dict(sd)
+        if missing:
+            msg = (f'{file}: {len(missing)} backbone/head tensors were not found in the checkpoint and keep their random '
+                   f'initialisation, e.g. {missing[:6]}')
+            if strict_report:
+                raise RuntimeError(msg)
+            warnings.warn(msg, stacklevel=2)
+        return missing
+
+    _KEY_ALIASES = tuple((f'downsample_stage_{i + 1}.', f'downsample_layers.{i}.') for i in range(3))
+
+    def load_flat_state_dict(self, sd):
+        """Fills ``backbone`` and ``head`` from a flat (un-prefixed or ``backbone.`` / ``head.``-prefixed) state_dict; returns
+        the list of own parameter/buffer names that stayed unfilled (``num_batches_tracked`` excluded)."""
+        flat = {}
+        for k, v in sd.items():
+            for pre in ('backbone.', 'head.'):
+                if k.startswith(pre):
+                    k = k[len(pre):]
+            for theirs, ours in self._KEY_ALIASES:
+                if k.startswith(theirs):
+                    k = ours + k[len(theirs):]
+            flat[k] = v
+        missing = []
+        for name, mod in (('backbone', self.backbone), ('head', self.head)):
+            own = mod.state_dict()
+            take = {k: v for k, v in flat.items() if k in own and own[k].shape == v.shape}
+            mod.load_state_dict(take, strict=False)
+            missing += [f'{name}.{k}' for k in own if k not in take and not k.endswith('num_batches_tracked')]
+        self._mark_dirty()
+        self.backbone.mark_dirty()
+        return missing
 
     # ---- engine
     def _mark_dirty(self):
@@ -182,11 +251,18 @@ class HMR(nn.Module):
         except Exception:
             pass
 
+    def _weights_changed(self):
+        """True when a parameter / buffer of the head or the SMPL layer was modified in place (optimizer step,
+        ``param.data.copy_``) since the folded weights were uploaded."""
+        w = getattr(self, '_watch', None)
+        return w is None or w.changed()
+
     def _ensure(self, device):
-        if self._handle is not None and not self._dirty and self._device == device:
+        if self._handle is not None and not self._dirty and self._device == device and not self._weights_changed():
             return
         _lib.require_device()
         self._release()
+        self._graphs.clear()
         hd, sm = self.head, self.smpl.smpl
         keep = []
 
@@ -221,6 +297,7 @@ class HMR(nn.Module):
         self._x_ld = int(_lib.lib().specb200_hmrtail_x_ld(h))
         self._device = device
         self._dirty = False
+        self._watch = _lib.VersionWatch(self.head, self.smpl)
 
     def _workspace(self, B, device):
         n = _lib.lib().specb200_hmrtail_workspace_bytes(self._handle, B)
@@ -245,6 +322,7 @@ class HMR(nn.Module):
         Small batches (the demo loop runs one forward per image with batch = #detections, spec/tester.py:143-151) are
         launch-bound (60 kernels of a few microseconds): for B <= ``graph_max_batch`` the forward is captured once per
         input shape into a CUDA graph and replayed (SPECB200_MODULE_GRAPH=0 disables)."""
+        _lib.refuse_training(self)
         if (_out is None and self._module_graph and images.is_cuda and images.shape[0] <= self.graph_max_batch
                 and images.shape[0] > 0 and not torch.cuda.is_current_stream_capturing()):
             return self._forward_graphed(images, cam_rotmat, cam_intrinsics, bbox_scale, bbox_center, img_w, img_h)
@@ -256,7 +334,7 @@ class HMR(nn.Module):
         args = {'cam_rotmat': (cam_rotmat, (3, 3)), 'cam_intrinsics': (cam_intrinsics, (3, 3)), 'bbox_scale': (bbox_scale, ()),
                 'bbox_center': (bbox_center, (2,)), 'img_w': (img_w, ()), 'img_h': (img_h, ())}
         key = (dev, tuple(images.shape), self.backbone.precision, tuple(k for k, (v, _) in args.items() if v is not None))
-        if self._dirty or self.backbone._dirty:
+        if self._dirty or self.backbone._dirty or self._weights_changed() or self.backbone._weights_changed():
             self._graphs.clear()                                   # weights changed: captured graphs hold stale handles
         g = self._graphs.get(key)
         if g is None:

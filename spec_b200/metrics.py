@@ -60,6 +60,10 @@ class EvalMetrics(nn.Module):
             pred_vertices = pred_vertices.float().contiguous()
         if gt_keypoints_3d is None and gt_vertices is None:
             raise ValueError('need gt_keypoints_3d or gt_vertices')
+        if center_v2v and gt_keypoints_3d is not None:
+            # the centred vertex error (compute_error.py) subtracts the pelvis regressed from BOTH meshes; with ground-truth
+            # keypoints supplied the kernel takes the joint errors from them and never regresses the GT pelvis
+            raise ValueError('center_v2v=True needs the joints regressed from gt_vertices: do not pass gt_keypoints_3d with it')
         self._ensure(dev)
         L = _lib.lib()
         kp = gt_keypoints_3d.to(dev, torch.float32).contiguous() if gt_keypoints_3d is not None else None

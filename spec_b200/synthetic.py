@@ -74,3 +74,21 @@ def synthetic_camera(batch, seed=0, img_h=1080., img_w=1920.):
     roll = torch.rand(batch, generator=g) * 1.2 - 0.6
     vfov = torch.rand(batch, generator=g) * (2.1 - 0.2617) + 0.2617
     return vfov, pitch, roll
+
+
+def synthetic_camera_matrices(batch, seed=0, img_h=1080., img_w=1920., device='cpu'):
+    """Dataset-supplied camera of the eval loop (BASELINE configs[3]; spec/trainer.py:235-236 ``batch['cam_rotmat']``,
+    ``batch['cam_int']``): R = Rx(pitch) Rz(roll), K = [[f,0,w/2],[0,f,h/2],[0,0,0]] with f = h/2/tan(vfov/2)
+    (K[2,2] stays 0 as spec/utils/cam_params.py:39-46 leaves it)."""
+    vfov, pitch, roll = synthetic_camera(batch, seed, img_h, img_w)
+    cp, sp, cr, sr = torch.cos(pitch), torch.sin(pitch), torch.cos(roll), torch.sin(roll)
+    z, o = torch.zeros_like(cp), torch.ones_like(cp)
+    Rx = torch.stack([o, z, z, z, cp, -sp, z, sp, cp], 1).view(-1, 3, 3)
+    Rz = torch.stack([cr, -sr, z, sr, cr, z, z, z, o], 1).view(-1, 3, 3)
+    f = img_h / 2. / torch.tan(vfov / 2.)
+    K = torch.zeros(batch, 3, 3)
+    K[:, 0, 0] = f
+    K[:, 1, 1] = f
+    K[:, 0, 2] = img_w / 2.
+    K[:, 1, 2] = img_h / 2.
+    return (Rx @ Rz).contiguous().to(device), K.to(device)

@@ -9,7 +9,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-warnings.filterwarnings('ignore', message='.*SYNTHETIC SMPL.*')
+# there is no network for the licensed SMPL files: the tests opt in to the seeded synthetic stand-ins explicitly
+# (without this variable a missing asset raises FileNotFoundError, tests/test_boundary.py::test_missing_assets_raise)
+os.environ.setdefault('SPECB200_SYNTHETIC_ASSETS', '1')
+warnings.filterwarnings('ignore', message='.*SYNTHETIC.*')
 warnings.filterwarnings('ignore', message='.*pretrained ImageNet.*')
 
 
@@ -24,6 +27,15 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if 'gpu' in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    """The product is inference-only and refuses ``training and grad-enabled`` forwards (spec_b200/_lib.py::refuse_training;
+    covered by tests/test_boundary.py::test_training_mode_forward_raises): the tests run under no_grad like every caller of
+    the reference's inference path (tester.py:143 ``with torch.no_grad()``)."""
+    with torch.no_grad():
+        yield
 
 
 # ---------------------------------------------------------------- shared builders (tests only)

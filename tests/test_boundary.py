@@ -5,6 +5,7 @@ import inspect
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -246,3 +247,99 @@ def test_header_is_plain_c_and_links(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.strip() == f'{len(names)} symbols'
+
+
+# ------------------------------------------------------------------------------------------- round-2 behaviours
+def test_missing_assets_raise(monkeypatch, tmp_path):
+    """Without an explicit opt-in a missing SMPL model / mean-parameter file raises like the reference does; the synthetic
+    stand-ins need SPECB200_SYNTHETIC_ASSETS=1 (or explicit smpl_data= / mean_params=)."""
+    from spec_b200 import hmr as H
+    monkeypatch.setenv('SPECB200_SYNTHETIC_ASSETS', '0')
+    monkeypatch.setattr(H, 'SMPL_MODEL_DIR', str(tmp_path / 'nope'))
+    monkeypatch.setattr(H, 'SMPL_MEAN_PARAMS', str(tmp_path / 'nope.npz'))
+    with pytest.raises(FileNotFoundError, match='SMPL'):
+        H.SMPL()
+    with pytest.raises(FileNotFoundError, match='SYNTHETIC_ASSETS'):
+        H.HMRHead(512)
+    with pytest.raises(FileNotFoundError):
+        sb.HMR('resnet34', use_cam=True, use_cam_feats=True)
+    from spec_b200.synthetic import synthetic_smpl_data, synthetic_mean_params
+    sb.HMR('resnet34', use_cam=True, use_cam_feats=True, smpl_data=synthetic_smpl_data(0), mean_params=synthetic_mean_params(0))   # explicit data: fine
+
+
+def test_smpl_pkl_and_npz_are_accepted(monkeypatch, tmp_path):
+    """A standard SPEC data directory ships SMPL_NEUTRAL.pkl (smplx); an .npz export works too (scipy-sparse J_regressor,
+    (6890,3,207) posedirs and 300 shape components are normalised to the smplx buffer shapes)."""
+    import pickle
+    import scipy.sparse as sp
+    from spec_b200 import hmr as H
+    from spec_b200.synthetic import synthetic_smpl_data
+    d = synthetic_smpl_data(3)
+    raw = {'v_template': d['v_template'].astype(np.float64), 'shapedirs': np.concatenate([d['shapedirs'], np.zeros((6890, 3, 2), np.float32)], 2),
+           'posedirs': d['posedirs'].T.reshape(6890, 3, 207), 'J_regressor': sp.csc_matrix(d['J_regressor']), 'weights': d['lbs_weights']}
+    mdir = tmp_path / 'smpl'
+    mdir.mkdir()
+    with open(mdir / 'SMPL_NEUTRAL.pkl', 'wb') as fh:
+        pickle.dump(raw, fh)
+    np.save(tmp_path / 'jx.npy', d['J_regressor_extra'])
+    monkeypatch.setenv('SPECB200_SYNTHETIC_ASSETS', '0')
+    monkeypatch.setattr(H, 'SMPL_MODEL_DIR', str(mdir))
+    monkeypatch.setattr(H, 'JOINT_REGRESSOR_TRAIN_EXTRA', str(tmp_path / 'jx.npy'))
+    got = H.SMPL()
+    for k in ('v_template', 'shapedirs', 'posedirs', 'J_regressor', 'lbs_weights', 'J_regressor_extra'):
+        assert torch.equal(getattr(got, k), torch.as_tensor(d[k]).float()), k
+
+
+def test_training_mode_forward_raises():
+    """Inference only: a forward in training mode with autograd enabled raises instead of silently training nothing."""
+    from spec_b200 import _lib
+    m = sb.CameraRegressorNetwork('resnet34')
+    with torch.enable_grad():
+        m.train()
+        with pytest.raises(RuntimeError, match='inference path only'):
+            _lib.refuse_training(m)
+        m.eval()
+        _lib.refuse_training(m)                          # eval mode: fine
+    m.train()
+    with torch.no_grad():
+        _lib.refuse_training(m)                          # no autograd: fine
+
+
+def test_checkpoint_loading_aliases_and_reports(tmp_path):
+    """HMR.load_pretrained is non-strict like the reference's (hmr.py:124-135) but REPORTS unfilled tensors; the HRNet tail is
+    accepted under both spellings (``downsample_layers.{i}`` here / ``downsample_stage_{i+1}`` believed upstream)."""
+    from spec_b200.synthetic import synthetic_smpl_data, synthetic_mean_params
+    kw = dict(use_cam=True, use_cam_feats=True, smpl_data=synthetic_smpl_data(0), mean_params=synthetic_mean_params(0))
+    src = sb.HMR('hrnet_w32-conv', **kw)
+    with torch.no_grad():
+        for p in src.backbone.parameters():
+            p.add_(1.0)
+    flat = {}
+    for k, v in list(src.backbone.state_dict().items()) + list(src.head.state_dict().items()):
+        for i in range(3):
+            k = k.replace(f'downsample_layers.{i}.', f'downsample_stage_{i + 1}.')
+        flat[k] = v.clone()
+    path = tmp_path / 'ckpt.pt'
+    torch.save({'model': flat}, path)
+    dst = sb.HMR('hrnet_w32-conv', **kw)
+    assert dst.load_pretrained(str(path)) == []
+    for (k, a), (_, b) in zip(src.backbone.state_dict().items(), dst.backbone.state_dict().items()):
+        assert torch.equal(a, b), k
+    # a checkpoint that lacks the tail: loud, not silent
+    torch.save({'model': {k: v for k, v in flat.items() if 'downsample_stage' not in k}}, path)
+    with pytest.raises(RuntimeError, match='downsample_layers'):
+        sb.HMR('hrnet_w32-conv', **kw).load_pretrained(str(path))
+    with pytest.warns(UserWarning, match='random'):
+        missing = sb.HMR('hrnet_w32-conv', **kw).load_pretrained(str(path), strict_report=False)
+    assert len(missing) == 6 * 5 and all('downsample_layers' in m for m in missing)
+
+
+def test_inplace_parameter_updates_are_noticed():
+    """Packed device copies are keyed on the tensors' in-place version counters (optimizer steps / param.data.copy_)."""
+    t = sb.backbone.resnet18()
+    assert t._weights_changed()                          # nothing packed yet
+    t._watch = sb._lib.VersionWatch(t)
+    assert not t._weights_changed()
+    with torch.no_grad():
+        t.layer1._modules['0'].conv1.weight.mul_(2.0)
+    assert t._weights_changed()

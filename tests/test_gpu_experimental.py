@@ -22,6 +22,6 @@ def test_opt_in_variant_keeps_parity(switch):
     env = dict(os.environ)
     env[switch] = '1'
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-x', '-q',
-                        '-k', 'conv_kernels or lowp_parity or golden or ragged or hrnet_bf16'],
-                       capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+                        '-k', 'conv_kernels or full_forward_lowp_parity or golden or ragged or bench_config'],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

@@ -79,6 +79,9 @@ CONV_CASES = [
     (128, 128, 3, 1, 1, True, 20, 30, 2),           # halo kernel, streamed weights (2 channel blocks), residual
     (256, 256, 3, 1, 1, False, 16, 17, 1),          # halo kernel, N=256 (two epilogue sub-tiles), 4 channel blocks
     (256, 512, 1, 1, 0, True, 9, 9, 3),             # persistent 1x1, N=256 tiles, residual
+    (32, 32, 3, 1, 1, True, 9, 11, 2),              # Cin=32 on an ODD width: the pixel-pair view does not apply -> gather-kernel fallback
+    (512, 512, 3, 1, 1, False, 14, 14, 56),         # CTA-pair kernel, im2col A, K=4608: 43 pair-tiles x 2 n-tiles = 86 tiles on 74 clusters (multi-tile loop)
+    (1024, 2048, 1, 1, 0, True, 7, 7, 200),         # CTA-pair kernel, 1x1: 39 pair-tiles x 8 n-tiles = 312 tiles on 74 clusters: the multi-tile loop + TMEM phase flips
 ]
 
 
@@ -242,15 +245,98 @@ def test_other_backbones_fp32(backbone):
     _assert_close('pred_cam', got['pred_cam'], want['pred_cam'], atol=1e-5, rtol=1e-5)
 
 
-def test_hrnet_bf16_runs_close():
-    hmr, ref = make_pair('hrnet_w32-conv', seed=4)
+# fp16 is not run for HRNet: with un-normalised random weights its activations grow past 65504 (features ~3e3 x a 20x stage-4
+# dynamic range), so the fp16 emulation AND the kernels overflow to inf -- a property of the synthetic weights, not of the path
+@pytest.mark.parametrize('backbone,precision', [('hrnet_w32-conv', 'bf16'), ('hrnet_w32-interp', 'bf16')])
+def test_hrnet_lowp_parity(backbone, precision):
+    """HRNet tensor-core path against the PRECISION-MATCHED oracle (oracle/lowp.py::hrnet_trunk_lowp rounds to 16 bits after
+    every op the CUDA path materialises).  What is left is fp32 summation order flipping isolated 16-bit roundings
+    (1 ulp = 2^-8 bf16 / 2^-11 fp16) that then propagate through ~150 layers: bound = a few ulps of the feature scale per
+    element and 1/4 ulp on average (the unmatched fp32 oracle differs by 7.5e-3 on average)."""
+    hmr, ref = make_pair(backbone, seed=4, amplify=False)
+    dt = TORCH_DT[precision]
+    b = synthetic_batch(2, seed=4)
+    feat_ref = lowp.hrnet_trunk_lowp(ref.backbone, b['images'], dt)
+    hmr.backbone.set_precision(precision)
+    feat = hmr.to(DEV).backbone(b['images'].to(DEV)).cpu()
+    scale = feat_ref.abs().mean().item()
+    ulp = 2.0 ** -8 if precision == 'bf16' else 2.0 ** -11
+    rel = ((feat - feat_ref).abs().mean() / scale).item()
+    print(f'{backbone} {precision}: mean rel err {rel:.3e}, max err / scale {((feat - feat_ref).abs().max() / scale).item():.3e}')
+    assert rel < 0.5 * ulp, rel
+    _assert_close(f'{backbone} features', feat, feat_ref, atol=8 * ulp * scale, rtol=8 * ulp)
+    vfov, pitch, roll = synthetic_camera(2, seed=4)
+    R, K, _ = og.cam_params_from_angles(vfov, pitch, roll, b['img_h'], b['img_w'])
+    want = lowp.hmr_lowp(ref, b['images'], R, K, b['bbox_scale'], b['bbox_center'], b['img_w'], b['img_h'], dt)
+    got = hmr(b['images'].to(DEV), R.to(DEV), K.to(DEV), b['bbox_scale'].to(DEV), b['bbox_center'].to(DEV), b['img_w'].to(DEV), b['img_h'].to(DEV))
+    _assert_close('smpl_vertices', got['smpl_vertices'], want['smpl_vertices'], atol=1e-2)
+    _assert_close('pred_cam', got['pred_cam'], want['pred_cam'], atol=5e-3, rtol=5e-3)
+
+
+def _layerwise_profile(prod_trunk, ref_trunk, images, dt, emulate):
+    """(conv name, mean rel err, max err / scale) of every conv op of the compiled program whose destination is a plain
+    activation buffer, CUDA path vs the traced precision-matched oracle."""
+    lowp.TRACE = {}
+    try:
+        emulate(ref_trunk, images, dt)
+        trace = dict(lowp.TRACE)
+    finally:
+        lowp.TRACE = None
+    mods = dict(ref_trunk.named_modules())
+    rows = []
+    P = prod_trunk._program
+    for i, o in enumerate(P.ops):
+        if o['type'] != 1 or o['dst_coff'] != 0 or P.buf_ch[o['dst']] != o['cout']:
+            continue
+        name = P.convs[o['wslot']][0]
+        want = trace.get(mods[name])
+        if want is None:
+            continue
+        got = prod_trunk.activation_after(images.to(DEV), i).cpu()
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        scale = want.abs().mean().item() + 1e-30
+        rows.append((name, ((got - want).abs().mean() / scale).item(), ((got - want).abs().max() / scale).item()))
+    return rows
+
+
+@pytest.mark.parametrize('backbone', ['resnet50', 'hrnet_w32-conv'])
+def test_layerwise_lowp_profile(backbone):
+    """EVERY intermediate conv output of the bf16 tensor-core path against the precision-matched oracle, layer by layer
+    (specb200_trunk_forward_until reads the activation buffers).  A kernel that rounds at a different point, drops a
+    bias or mis-handles a border shows up as a jump at ITS layer; what accumulates smoothly is rounding-boundary flips."""
+    hmr, ref = make_pair(backbone, seed=4, amplify=False)
     x = synthetic_batch(2, seed=4)['images']
+    hmr.backbone.set_precision('bf16')
+    hmr.to(DEV)
+    rows = _layerwise_profile(hmr.backbone, ref.backbone, x, torch.bfloat16, lowp.trunk_lowp)
+    assert len(rows) > 40
+    worst = 0.0
+    prev = 0.0
+    for name, mean_rel, max_rel in rows:
+        jump = mean_rel - prev
+        print(f'{name:40s} mean rel {mean_rel:.3e}  max/scale {max_rel:.3e}  {"<-- jump" if jump > 1e-3 else ""}')
+        worst = max(worst, mean_rel)
+        prev = mean_rel
+    ulp = 2.0 ** -8
+    assert worst < 0.5 * ulp, worst
+
+
+def test_hrnet_w48_runs_on_gpu():
+    """The W48 program (f4 ctor variant) on the device: fp32 parity of the trunk features, finite bf16 features of the same
+    shape within the lowp bound."""
+    hmr, ref = make_pair('hrnet_w48-conv', seed=8, amplify=False)
+    x = synthetic_batch(1, seed=8)['images']
     with torch.no_grad():
         feat_ref = ref.backbone(x)
-    hmr.backbone.set_precision('bf16')
+    hmr.backbone.set_precision('fp32')
     feat = hmr.to(DEV).backbone(x.to(DEV))
-    rel = ((feat.cpu() - feat_ref).abs().mean() / feat_ref.abs().mean()).item()
-    assert rel < 0.05, rel
+    assert feat.shape == (1, 720, 7, 7)
+    _assert_close('w48 features fp32', feat, feat_ref, atol=1e-3 * feat_ref.abs().mean().item(), rtol=1e-3)
+    hmr.backbone.set_precision('bf16')
+    f16 = hmr.backbone(x.to(DEV)).cpu()
+    want = lowp.hrnet_trunk_lowp(ref.backbone, x, torch.bfloat16)
+    s = want.abs().mean().item()
+    _assert_close('w48 features bf16', f16, want, atol=8 * 2.0 ** -8 * s, rtol=8 * 2.0 ** -8)
 
 
 def test_camcalib_module_forward_and_variable_size():
@@ -331,6 +417,120 @@ def test_batch_composition_invariance_at_full_size(models):
     R = out_big['pred_pose'].reshape(-1, 3, 3)
     assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3, device=R.device).expand_as(R), atol=1e-5)
     assert torch.isfinite(out_big['smpl_vertices']).all()
+
+
+def _lowp_reference(cc_ref, hmr_ref, b, idx, dt):
+    """Precision-matched oracle of the full SPEC step for the images ``idx`` of batch ``b``."""
+    sub = {k: v[idx] for k, v in b.items()}
+    lg = lowp.camcalib_lowp(cc_ref, sub['images'], dt)
+    vfov, pitch, roll = og.convert_preds_to_angles(*lg)
+    R, K, _ = og.cam_params_from_angles(vfov, pitch, roll, sub['img_h'], sub['img_w'])
+    ref = lowp.hmr_lowp(hmr_ref, sub['images'], R, K, sub['bbox_scale'], sub['bbox_center'], sub['img_w'], sub['img_h'], dt)
+    ref['cam_angles'] = torch.stack([vfov, pitch, roll], 1)
+    return ref
+
+
+@pytest.mark.parametrize('precision,B,n_oracle', [('bf16', 256, 32), ('fp16', 64, 16)], ids=['C3-bf16-b256', 'C2-fp16-b64'])
+def test_bench_config_under_oracle(models, precision, B, n_oracle):
+    """The BENCHMARKED configurations (BASELINE.json configs[2] = bf16 batch 256, configs[1] = fp16 batch 64), run exactly as
+    bench.py runs them (SPECPipeline CUDA-graph replay), with EVERY image checked: (a) image by image bit-equal to B=4
+    eager runs of the same images (B/4 runs) -- at B=256 the persistent / CTA-pair kernels loop over several tiles per
+    CTA (TMEM double-buffer phase flips, remote tempty arrives), at B=4 they do not; (b) ``n_oracle`` images spread over the
+    batch against the precision-matched CPU oracle (oracle/lowp.py), same tolerances as test_full_forward_lowp_parity."""
+    cc, cc_ref, hmr, hmr_ref = models
+    dt = TORCH_DT[precision]
+    b = synthetic_batch(B, seed=31)
+    big = _run_product(cc, hmr, b, precision, graph=True)
+    big2 = _run_product(cc, hmr, b, precision, graph=True)
+    for k in big:
+        assert torch.isfinite(big[k]).all(), k
+        assert torch.equal(big[k], big2[k]), k                           # replay is deterministic
+    for i0 in range(0, B, 4):
+        small = _run_product(cc, hmr, {k: v[i0:i0 + 4] for k, v in b.items()}, precision, graph=False)
+        for k in big:
+            assert torch.equal(big[k][i0:i0 + 4], small[k]), (k, i0)
+    idx = list(range(0, B, B // n_oracle))
+    ref = _lowp_reference(cc_ref, hmr_ref, b, idx, dt)
+    _assert_close('cam angles', big['cam_angles'][idx], ref['cam_angles'], atol=2e-3)
+    _assert_close('pred_cam', big['pred_cam'][idx], ref['pred_cam'], atol=5e-3, rtol=5e-3)
+    _assert_close('smpl_vertices', big['smpl_vertices'][idx], ref['smpl_vertices'], atol=1e-2)
+    _assert_close('smpl_joints3d', big['smpl_joints3d'][idx], ref['smpl_joints3d'], atol=1e-2)
+    _assert_close('pred_pose', big['pred_pose'][idx], ref['pred_pose'], atol=1e-2)
+    _assert_close('pred_shape', big['pred_shape'][idx], ref['pred_shape'], atol=5e-3, rtol=5e-3)
+
+
+def test_c4_eval_loop_batch_under_oracle(models):
+    """BASELINE.json configs[3] (SPEC-SYN-shaped eval loop; /root/reference/spec/trainer.py:235-245): CamCalib is bypassed --
+    the dataset supplies pre-computed cam_rotmat / cam_int -- and ``img_h`` / ``img_w`` are the int64 columns of
+    ``batch['orig_shape']``; batch 128 per GPU, bf16.  Checked like the bench config: bit-equal to B=4 runs, 16 images
+    against the precision-matched oracle."""
+    _, _, hmr, hmr_ref = models
+    B = 128
+    b = synthetic_batch(B, seed=41)
+    vfov, pitch, roll = synthetic_camera(B, seed=41)
+    R, K, _ = og.cam_params_from_angles(vfov, pitch, roll, b['img_h'], b['img_w'])
+    orig_shape = torch.stack([b['img_h'], b['img_w']], 1).long()          # cam_dataset.py:350,486
+    hmr.backbone.set_precision('bf16')
+    hmr.to(DEV)
+    def run(sl):
+        o = hmr(b['images'][sl].to(DEV), R[sl].to(DEV), K[sl].to(DEV), b['bbox_scale'][sl].to(DEV), b['bbox_center'][sl].to(DEV),
+                orig_shape[sl, 1].to(DEV), orig_shape[sl, 0].to(DEV))
+        torch.cuda.synchronize()
+        return o
+    big = run(slice(0, B))
+    for i0 in range(0, B, 4):
+        small = run(slice(i0, i0 + 4))
+        for k in big:
+            assert torch.equal(big[k][i0:i0 + 4], small[k]), (k, i0)
+    idx = list(range(0, B, 8))
+    ref = lowp.hmr_lowp(hmr_ref, b['images'][idx], R[idx], K[idx], b['bbox_scale'][idx], b['bbox_center'][idx],
+                        orig_shape[idx, 1], orig_shape[idx, 0], torch.bfloat16)
+    _assert_close('pred_cam', big['pred_cam'][idx], ref['pred_cam'], atol=5e-3, rtol=5e-3)
+    _assert_close('smpl_vertices', big['smpl_vertices'][idx], ref['smpl_vertices'], atol=1e-2)
+    _assert_close('pred_pose', big['pred_pose'][idx], ref['pred_pose'], atol=1e-2)
+    _assert_close('pred_cam_t', big['pred_cam_t'][idx], ref['pred_cam_t'], atol=2e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize('case', ['spec_resnet50', 'spec_hrnet_w32_conv', 'hmr_resnet34_nocam'])
+def test_against_reference_wrapper_fixture(case):
+    """CUDA fp32 path vs tests/golden/reference_wrappers.npz -- outputs of the reference's OWN wrapper code
+    (camcalib/model.py, spec/models/hmr.py, cam_utils.py, cam_params.py executed unmodified, pare stubbed;
+    tests/golden/reference_wrappers.py).  North-star tolerances: vertices 1e-3, camera parameters 1e-5."""
+    from tests.golden import reference_wrappers as rw
+    fx = np.load(rw.FIXTURE)
+    T = lambda k: torch.from_numpy(fx[f'{case}/{k}'])
+    cfg = rw.CASES[case]
+    seed = 40 + list(rw.CASES).index(case)
+    cc_o, hmr_o = rw.oracle_models(cfg, seed)
+    b = rw.case_inputs(cfg, seed)
+    hmr = sb.HMR(cfg['hmr'], use_cam=cfg['use_cam'], use_cam_feats=cfg['use_cam_feats'])
+    hmr.load_state_dict(hmr_o.state_dict(), strict=True)
+    hmr.backbone.set_precision('fp32')
+    hmr.to(DEV)
+    if cfg['camcalib']:
+        cc = sb.CameraRegressorNetwork(cfg['camcalib'], num_fc_layers=cfg['fc_layers'])
+        cc.load_state_dict(cc_o.state_dict(), strict=True)
+        cc.backbone.set_precision('fp32')
+        cc.to(DEV)
+        logits = cc(b['images'].to(DEV))
+        for n, l in zip(('vfov', 'pitch', 'roll'), logits):       # fp32 GEMM chains (3 layers deep in one case): 1e-5 of the logit scale
+            _assert_close('logits ' + n, l, T('logits_' + n), atol=1e-5 * T('logits_' + n).abs().mean().item() + 5e-5, rtol=1e-4)
+        ang, R, K, _ = cc.predict_camera(b['images'].to(DEV), b['img_h'].to(DEV), b['img_w'].to(DEV))
+        _assert_close('angles', ang, torch.stack([T('cam_vfov'), T('cam_pitch'), T('cam_roll')], 1), atol=1e-5)
+        _assert_close('R', R, T('cam_rotmat'), atol=1e-5)
+        _assert_close('K', K, T('cam_intrinsics'), atol=1e-2, rtol=1e-5)
+        assert (K[:, 2, 2] == 0).all()
+        got = hmr(b['images'].to(DEV), R, K, b['bbox_scale'].to(DEV), b['bbox_center'].to(DEV), b['img_w'].to(DEV), b['img_h'].to(DEV))
+    else:
+        got = hmr(b['images'].to(DEV))
+    assert list(got.keys()) == list(fx[f'{case}/keys'])
+    _assert_close('smpl_vertices', got['smpl_vertices'], T('hmr_smpl_vertices'), atol=1e-3)
+    _assert_close('smpl_joints3d', got['smpl_joints3d'], T('hmr_smpl_joints3d'), atol=1e-3)
+    _assert_close('pred_cam', got['pred_cam'], T('hmr_pred_cam'), atol=1e-5, rtol=1e-5)
+    _assert_close('pred_shape', got['pred_shape'], T('hmr_pred_shape'), atol=1e-4, rtol=1e-4)
+    _assert_close('pred_pose', got['pred_pose'], T('hmr_pred_pose'), atol=1e-4)
+    _assert_close('pred_cam_t', got['pred_cam_t'], T('hmr_pred_cam_t'), atol=1e-3, rtol=1e-4)
+    _assert_close('smpl_joints2d', got['smpl_joints2d'], T('hmr_smpl_joints2d'), atol=0.05, rtol=1e-3)
 
 
 # --------------------------------------------------------------------------------------- edge cases
