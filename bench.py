@@ -286,11 +286,28 @@ def run_ours(a):
 
     gatherer, gather_desc = (sb.make_gatherer(B, dev) if world > 1 else (None, None))
 
+    c4_graphs = {}
+
     @torch.no_grad()
     def compute(inp=None, bound=False):
         if c4:                                                     # trainer.py:235-245 call, outputs written into the packed record
             im = inp['images'] if inp is not None else b['images']
-            hmr(im, R, K, b['bbox_scale'], b['bbox_center'], orig_shape[:, 1], orig_shape[:, 0], _out=c4_out)
+            run = lambda: hmr(im, R, K, b['bbox_scale'], b['bbox_center'], orig_shape[:, 1], orig_shape[:, 0], _out=c4_out)
+            if a.no_graph:
+                run()
+                return c4_rec
+            g = c4_graphs.get(im.data_ptr())                       # one CUDA graph per (static) input buffer, like SPECPipeline
+            if g is None:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    run(); run()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                g = c4_graphs[im.data_ptr()] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run()
+            g.replay()
             return c4_rec
         if inp is None:
             return pipe.forward_packed(*args)
@@ -321,7 +338,10 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
         e0.record()
+        t_host0 = time.perf_counter()
+        host_ms = []
         for i in range(steps):
+            host_ms.append((time.perf_counter() - t_host0) * 1e3)  # when the launching thread STARTED enqueuing step i
             fn()
             marks[i].record()
             if mid is not None and i % 64 == min(steps // 2, 32):
@@ -335,7 +355,8 @@ def run_ours(a):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         raw = [a_.elapsed_time(b_) for a_, b_ in zip([e0] + marks[:-1], marks)]
         per = sorted(raw)
-        timed.step_ms = {'min': per[0], 'median': per[len(per) // 2], 'max': per[-1], 'argmax': raw.index(per[-1])}
+        timed.step_ms = {'min': per[0], 'median': per[len(per) // 2], 'max': per[-1], 'argmax': raw.index(per[-1]),
+                         'first_step_ms': raw[0], 'host_enqueue_start_ms': [round(h, 3) for h in host_ms[:4]]}
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)             # max over ranks
         return ms.item()

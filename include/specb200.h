@@ -91,6 +91,9 @@ int specb200_trunk_forward_until(specb200_trunk_t* t, const float* images_nchw_d
 /* number of kernels the last forward enqueued (bench.py's gpu_launches) */
 int64_t specb200_trunk_last_launches(specb200_trunk_t* t);
 int32_t specb200_trunk_num_ops(specb200_trunk_t* t);
+/* number of [downsample] conv1x1-conv3x3-conv1x1 bottleneck groups of the program that run as ONE fused launch
+ * (64 mid channels, 256 outputs, stride 1: ResNet-50 / HRNet layer1; 16-bit modes only) */
+int32_t specb200_trunk_num_fused_bottlenecks(specb200_trunk_t* t);
 /* Diagnostic variant of specb200_trunk_forward: brackets every op with CUDA events on `stream`, SYNCHRONISES, and
  * writes per-op device milliseconds to op_ms_host[0 .. n_ops+1] (0 = image NCHW->NHWC conversion, 1..n_ops = ops in
  * program order, n_ops+1 = average pool), summed over batch chunks.  Used by bench.py for the live roofline. */

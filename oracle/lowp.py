@@ -27,17 +27,26 @@ def fold_bn(conv, bn):
 TRACE = None      # tests may set this to a dict: conv module -> emulated output (layer-wise comparison with the CUDA path)
 
 
-def conv_bn_act(x, conv, bn, dtype, relu, res=None):
+def conv_bn_act(x, conv, bn, dtype, relu, res=None, keep_fp32=False):
     w, b = fold_bn(conv, bn)
     y = F.conv2d(x, _rnd(w, dtype), None, conv.stride, conv.padding) + b.view(1, -1, 1, 1)
     if res is not None:
         y = y + res
     if relu:
         y = torch.relu(y)
-    y = _rnd(y, dtype)
+    if not keep_fp32:
+        y = _rnd(y, dtype)
     if TRACE is not None:
         TRACE[conv] = y
     return y
+
+
+def _fused_downsample(blk):
+    """The 64 -> 64 -> 256 stride-1 bottleneck WITH a downsample conv (ResNet-50 / HRNet layer1.0) runs as one kernel
+    (spec_b200/csrc/conv_bneck.cu) in which the downsample conv and conv3 share ONE fp32 accumulator: the identity branch is
+    never rounded to 16 bits on its own.  (Everything else rounds after every conv, fused or not.)"""
+    return (blk.downsample is not None and isinstance(blk, Bottleneck) and blk.conv1.in_channels == 64 and blk.conv1.out_channels == 64
+            and blk.conv3.out_channels == 256 and blk.conv2.stride == (1, 1) and blk.downsample[0].stride == (1, 1))
 
 
 @torch.no_grad()
@@ -47,15 +56,11 @@ def resnet_trunk_lowp(trunk, images, dtype=torch.bfloat16):
     x = F.max_pool2d(x, 3, 2, 1)
     for layer in (trunk.layer1, trunk.layer2, trunk.layer3, trunk.layer4):
         for blk in layer:
-            idt = x if blk.downsample is None else conv_bn_act(x, blk.downsample[0], blk.downsample[1], dtype, False)
             if isinstance(blk, Bottleneck):
-                t = conv_bn_act(x, blk.conv1, blk.bn1, dtype, True)
-                t = conv_bn_act(t, blk.conv2, blk.bn2, dtype, True)
-                x = conv_bn_act(t, blk.conv3, blk.bn3, dtype, True, res=idt)
+                x = _bottleneck_lowp(blk, x, dtype)
             else:
                 assert isinstance(blk, BasicBlock)
-                t = conv_bn_act(x, blk.conv1, blk.bn1, dtype, True)
-                x = conv_bn_act(t, blk.conv2, blk.bn2, dtype, True, res=idt)
+                x = _basic_block_lowp(blk, x, dtype)
     return x
 
 
@@ -66,7 +71,8 @@ def _basic_block_lowp(blk, x, dtype):
 
 
 def _bottleneck_lowp(blk, x, dtype):
-    idt = x if blk.downsample is None else conv_bn_act(x, blk.downsample[0], blk.downsample[1], dtype, False)
+    idt = x if blk.downsample is None else conv_bn_act(x, blk.downsample[0], blk.downsample[1], dtype, False,
+                                                       keep_fp32=_fused_downsample(blk) and dtype != torch.float32)
     t = conv_bn_act(x, blk.conv1, blk.bn1, dtype, True)
     t = conv_bn_act(t, blk.conv2, blk.bn2, dtype, True)
     return conv_bn_act(t, blk.conv3, blk.bn3, dtype, True, res=idt)

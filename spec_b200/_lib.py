@@ -60,6 +60,7 @@ _PROTOS = {
                                                _I, _I, _I, C.c_void_p, C.c_void_p]),
     'specb200_trunk_last_launches': (C.c_int64, [C.c_void_p]),
     'specb200_trunk_num_ops': (C.c_int32, [C.c_void_p]),
+    'specb200_trunk_num_fused_bottlenecks': (C.c_int32, [C.c_void_p]),
     'specb200_trunk_profile': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'specb200_trunk_destroy': (None, [C.c_void_p]),
@@ -131,15 +132,27 @@ def check(rc):
         raise RuntimeError('libspecb200: ' + lib().specb200_last_error().decode())
 
 
+_device_ok = set()
+
+
 def require_device(t=None):
-    """The product has no CPU path: refuse anything but a CUDA sm_100 tensor/device."""
+    """The product has no CPU path: refuse anything but a CUDA sm_100 tensor/device.  The architecture check is made once
+    per device (it is a driver query; on the hot path it cost milliseconds per call and blocked behind nvidia-smi pollers)."""
     import torch
     if t is not None and not t.is_cuda:
         raise RuntimeError('spec_b200 has no CPU path: tensors must live on a CUDA sm_100 (B200) device '
                            f'(got {t.device})')
+    key = t.device.index if t is not None else -1
+    if key in _device_ok:
+        return
     if not torch.cuda.is_available():
         raise RuntimeError('spec_b200 has no CPU path: no CUDA device available')
-    check(lib().specb200_device_check())
+    if t is not None:
+        with torch.cuda.device(t.device):
+            check(lib().specb200_device_check())
+    else:
+        check(lib().specb200_device_check())
+    _device_ok.add(key)
 
 
 def refuse_training(module):

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libspecb200.so')
 STAMP = os.path.join(HERE, '.libspecb200.stamp')
-SOURCES = ['api.cu', 'conv_tc.cu', 'conv_halo.cu', 'conv_stem.cu', 'conv_simt.cu', 'elementwise.cu', 'tail.cu', 'eval.cu', 'preprocess.cu', 'gather.cu']
+SOURCES = ['api.cu', 'conv_tc.cu', 'conv_halo.cu', 'conv_bneck.cu', 'conv_stem.cu', 'conv_simt.cu', 'elementwise.cu', 'tail.cu', 'eval.cu', 'preprocess.cu', 'gather.cu']
 HEADERS = ['common.cuh', 'internal.h', 'tail.h', 'conv_tc2.cuh', os.path.join('..', '..', 'include', 'specb200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--threads', '4']

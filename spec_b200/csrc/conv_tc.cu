@@ -719,6 +719,10 @@ static bool make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_
     return true;
 }
 
+bool make_tmap_2d_k64(CUtensorMap* m, const void* ptr, int rows, int ld, int box_rows) {
+    return make_tmap_2d(m, ptr, static_cast<uint64_t>(rows), static_cast<uint64_t>(ld), static_cast<uint64_t>(ld), static_cast<uint32_t>(box_rows));
+}
+
 // NHWC activation tensor in im2col mode: 64 channels x 128 output pixels per load.
 static bool make_tmap_im2col(CUtensorMap* m, const ConvParams& p) {
     static EncodeIm2colFn fn = nullptr;

@@ -74,6 +74,19 @@ bool conv_halo_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaS
 // 4-D tiled TMA descriptor over an NHWC 16-bit tensor: box = 64 channels x box_w x box_h x 1, 128-byte swizzle (conv_halo.cu)
 bool make_tmap_nhwc(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int N, int box_w, int box_h);
 
+// 2-D 16-bit K-major matrix [rows][ld] (ld elements per row): box = 64 columns x box_rows rows, 128-byte swizzle (conv_tc.cu)
+bool make_tmap_2d_k64(CUtensorMap* m, const void* ptr, int rows, int ld, int box_rows);
+
+// whole 64-channel bottleneck in one launch (conv_bneck.cu): y = relu(conv3(relu(conv2(relu(conv1(x))))) + (wd ? wd(x) : x))
+struct BottleneckArgs {
+    const void* x = nullptr;      // NHWC [N][H][W][Cin], Cin = 256 (identity residual) or 64 (with downsample conv wd)
+    void* out = nullptr;          // NHWC [N][H][W][256]
+    int N = 0, H = 0, W = 0, Cin = 0;
+    const ConvWeights *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wd = nullptr;
+};
+bool bottleneck_applicable(const BottleneckArgs& a);
+bool bottleneck_launch(const BottleneckArgs& a, int prec, cudaStream_t s);
+
 // dedicated 7x7/2 stem (conv_stem.cu): reads the fp32 NCHW image directly, writes NHWC 16-bit [N,Ho,Wo,64]
 bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N, int H, int W, int Ho, int Wo, int prec,
                        cudaStream_t s);

@@ -1,13 +1,13 @@
 #!/bin/bash
 # ncu evidence for profiles/: (1) launch list with per-launch device time of exactly one bench step (eager, no graph),
-# (2) one --set full capture of every conv launch of one trunk (the .ncu-rep stays on the box; the raw and
+# (2) one --set full capture of every conv-family launch (conv_*, conv3x3_halo, bottleneck64) of ONE STEP = both trunks (the .ncu-rep stays on the box; the raw and
 # source-counter CSV pages come back).  1 GPU only.  Numbers under ncu are never bench values.
 set -x
 mkdir -p gpurun_out
 TAG=${1:-r01}
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --profile-range > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
-ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_ -c 56 -o /tmp/conv_${TAG} -f \
+ncu --profile-from-start off --set full --clock-control none --import-source on -k 'regex:conv|bottleneck' -c 120 -o /tmp/conv_${TAG} -f \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --profile-range > gpurun_out/ncu_full_${TAG}.log 2>&1
 ncu -i /tmp/conv_${TAG}.ncu-rep --page raw --csv > gpurun_out/conv_${TAG}_raw.csv 2>/dev/null
 ncu -i /tmp/conv_${TAG}.ncu-rep --page details --csv 2>/dev/null | grep -E "Duration|Throughput|Tensor|Registers|Warp Cycles|Theoretical Occ|Achieved Occ|Shared Memory Config|Block Limit" | head -400 > gpurun_out/conv_${TAG}_details.csv

@@ -32,7 +32,8 @@ out.append(f'{n_launch} launches, {tot/1e6:.3f} ms total under ncu\n')
 out.append('| kernel | launches | total us | share |\n|---|---:|---:|---:|')
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f'| `{k}` | {v[0]} | {v[1]/1e3:.1f} | {100*v[1]/tot:.1f}% |')
-conv_share = sum(v[1] for k, v in agg.items() if k.startswith('conv_')) / tot
+is_conv = lambda k: k.lstrip().startswith('conv') or 'bottleneck' in k          # conv_tc*, conv_tcp*, conv_stem7*, conv3x3_halo, bottleneck64
+conv_share = sum(v[1] for k, v in agg.items() if is_conv(k)) / tot
 out.append(f'\nconv kernels share of the step: **{100*conv_share:.1f}%**\n')
 
 # ---- full capture
@@ -47,7 +48,7 @@ want = [('Kernel Name', 'kernel'), ('launch__grid_size', 'grid'), ('gpu__time_du
         ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'SM %'),
         ('launch__registers_per_thread', 'regs'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps active %')]
 want = [(a, b) for a, b in want if a in col]
-out.append('## `ncu --set full` of the conv launches of one trunk (first 56 conv launches of the step)\n')
+out.append('## `ncu --set full` of the conv-family launches of ONE step (both trunks)\n')
 out.append('| # | ' + ' | '.join(b for _, b in want) + ' |\n|---|' + '---|' * len(want))
 def short(n):
     n = n.replace('void sb::', '').replace('__nv_bfloat16', 'bf16')
@@ -73,7 +74,14 @@ for i, r in enumerate(rows[2:]):
         pass
 if tens:
     tt = sum(t for t, _, _ in tens)
+    total_bytes = sum(b for _, _, b in tens)
     out.append(f'\ntime-weighted tensor-pipe utilisation over these launches: **{sum(t*p for t,p,_ in tens)/tt:.1f}%**; '
-               f'DRAM traffic {sum(b for _,_,b in tens)/1e3:.2f} GB per trunk (algorithmic minimum 13.5 GB fused-epilogue, SURVEY B.2)\n')
+               f'DRAM traffic {total_bytes/1e9:.2f} GB per step over {len(tens)} conv-family launches\n')
+    # bench.py reads roofline.traffic from this file (key = backbone|batch|precision of the captured command)
+    key = sys.argv[2] if len(sys.argv) > 2 else 'resnet50|256|bf16'
+    tp = 'profiles/ncu_traffic.json'
+    d = json.load(open(tp)) if os.path.exists(tp) else {}
+    d[key] = {'bytes_per_step': total_bytes, 'launches': len(tens), 'source': f'profiles/ncu_{tag}.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)'}
+    json.dump(d, open(tp, 'w'), indent=1)
 open(f'profiles/ncu_{tag}.md', 'w').write('\n'.join(out) + '\n')
 print('\n'.join(out[:40]))
