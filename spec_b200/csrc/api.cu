@@ -239,6 +239,7 @@ static bool pack_conv(specb200_trunk* t, ConvWeights& w, bool stem7, const float
     w.K = kh * kw * cin_s;
     if (!check_cuda(cudaMalloc(&w.bias, sizeof(float) * cout), "cudaMalloc bias")) return false;
     if (!check_cuda(cudaMemcpy(w.bias, b_host, sizeof(float) * cout, cudaMemcpyHostToDevice), "bias upload")) return false;
+    w.bias_host.assign(b_host, b_host + cout);
     auto to16 = [&](float v) {
         uint16_t bits;
         if (t->prec == PREC_BF16) { __nv_bfloat16 h = __float2bfloat16_rn(v); memcpy(&bits, &h, 2); }

@@ -281,7 +281,16 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static bool make_tmap_nhwc_impl(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int N, int box_c, int box_w, int box_h, bool swizzle128);
+
 bool make_tmap_nhwc(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int N, int box_w, int box_h) {
+    return make_tmap_nhwc_impl(m, ptr, C_ld, W, H, N, 64, box_w, box_h, true);
+}
+bool make_tmap_nhwc_plain(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int N, int box_c, int box_w, int box_h) {
+    return make_tmap_nhwc_impl(m, ptr, C_ld, W, H, N, box_c, box_w, box_h, false);
+}
+
+static bool make_tmap_nhwc_impl(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int N, int box_c, int box_w, int box_h, bool swizzle128) {
     static EncodeTiledFn4 fn = nullptr;
     if (!fn) {
         void* q = nullptr;
@@ -294,10 +303,11 @@ bool make_tmap_nhwc(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int
     }
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(C_ld), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(C_ld) * 2, static_cast<cuuint64_t>(W) * C_ld * 2, static_cast<cuuint64_t>(H) * W * C_ld * 2};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(4d) failed (code " + std::to_string(static_cast<int>(r)) + ")"); return false; }
     return true;
 }

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 namespace sb {
 
@@ -35,6 +36,7 @@ struct ConvWeights {
     void* w_tc = nullptr;      // [cout_pad][K_pad] 16-bit, K-major (tcgen05 path)
     float* w_f32 = nullptr;    // [K][cout] fp32 (SIMT parity path)
     float* bias = nullptr;     // [cout]
+    std::vector<float> bias_host;   // same values on the host (kernels that take their biases as launch parameters)
     CUtensorMap tmap_b;        // TMA descriptor over w_tc (box 64 x block_n, 128B swizzle)
     bool has_tmap = false;
 };
@@ -73,6 +75,8 @@ bool conv_halo_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaS
 
 // 4-D tiled TMA descriptor over an NHWC 16-bit tensor: box = 64 channels x box_w x box_h x 1, 128-byte swizzle (conv_halo.cu)
 bool make_tmap_nhwc(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int N, int box_w, int box_h);
+// same tensor, box = box_c channels x box_w x box_h x 1 WITHOUT swizzle (dense rows of box_c * 2 bytes in shared memory)
+bool make_tmap_nhwc_plain(CUtensorMap* m, const void* ptr, int C_ld, int W, int H, int N, int box_c, int box_w, int box_h);
 
 // 2-D 16-bit K-major matrix [rows][ld] (ld elements per row): box = 64 columns x box_rows rows, 128-byte swizzle (conv_tc.cu)
 bool make_tmap_2d_k64(CUtensorMap* m, const void* ptr, int rows, int ld, int box_rows);
