@@ -244,12 +244,14 @@ bool smpl_prep_launch(const float* X, int ldx, int C, const float* Jt, const flo
 }
 
 // ------------------------------------------------------------------ SMPL vertices
-// Tile: 64 vertices x 32 images per CTA; 256 threads: lane -> vertices (lane, lane+32), warp -> 4 images.
+// Tile: 64 vertices x 32 images per CTA; 256 threads: lane -> the adjacent vertices (2*lane, 2*lane+1), warp -> 4 images.
+// (Adjacent vertices + a transposed pose-feature chunk turn the 10 scalar shared-memory loads per k of the pose-blend loop --
+// it was LDS-bound: 10 LDS per 24 FFMA -- into one LDS.128 and three LDS.64.)
 constexpr int SV_TV = 64, SV_TB = 32, SV_BK = 16;
 struct SvSmem {
     float A[SV_TB][24][12];          // skinning transforms of the tile's images (36 KB)
     float P[SV_BK][3][SV_TV];        // posedirs chunk (12 KB)
-    float pf[SV_TB][SV_BK];          // pose-feature chunk
+    float pf[SV_BK][SV_TB];          // pose-feature chunk, [k][image]
     float beta[SV_TB][10];
 };
 
@@ -300,16 +302,19 @@ smpl_verts_kernel(const float* __restrict__ Vt, const float* __restrict__ Sd, co
             const int bi = tid >> 2, kq = (tid & 3) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (b0 + bi < B) v = *reinterpret_cast<const float4*>(pf + static_cast<size_t>(b0 + bi) * PF_LD + k0 + kq);
-            *reinterpret_cast<float4*>(&sm.pf[bi][kq]) = v;
+            sm.pf[kq + 0][bi] = v.x; sm.pf[kq + 1][bi] = v.y; sm.pf[kq + 2][bi] = v.z; sm.pf[kq + 3][bi] = v.w;
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < SV_BK; ++kk) {
-            float a[4], p[3][2];
+            float p[3][2];
+            const float4 a4 = *reinterpret_cast<const float4*>(&sm.pf[kk][warp * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = sm.pf[warp * 4 + i][kk];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { p[c][0] = sm.P[kk][c][lane]; p[c][1] = sm.P[kk][c][lane + 32]; }
+            for (int c = 0; c < 3; ++c) {
+                const float2 p2 = *reinterpret_cast<const float2*>(&sm.P[kk][c][2 * lane]);
+                p[c][0] = p2.x; p[c][1] = p2.y;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -327,7 +332,7 @@ smpl_verts_kernel(const float* __restrict__ Vt, const float* __restrict__ Sd, co
 
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int v = v0 + lane + 32 * h;
+        const int v = v0 + 2 * lane + h;
         // shape blendshapes
         float vs[4][3];
 #pragma unroll
