@@ -68,16 +68,15 @@ struct ConvTcMaps {
     CUtensorMap res;    // EPI_TMA + residual: [M][res_ld] box 64 x 128
 };
 
-// MCAST (experiment, SPECB200_MCAST_B=1, TMA-fed modes only): clusters of two CTAs work on two M tiles of the SAME n tile; each
-// loads half of the weight tile per k-block and multicasts it into both CTAs, so a CTA fetches A 16 KB + B/2 per k-block
-// (tools/tma_mcast_test.cu: a 2-CTA multicast lands 9.1 TB/s of HBM-streamed tiles against 6.1 TB/s without).  A stage may be
-// refilled only when BOTH CTAs' MMAs have retired it: the stage-release commit is multicast to both empty barriers (count 2).
-template <typename T, int BLOCK_N, int STAGES, int A_MODE, bool MCAST = false>
+// (A variant of this kernel in clusters of two CTAs that shared the weight tile by TMA multicast -- each CTA loading half of it per
+// k-block, stage release by a multicast commit onto both empty barriers -- was written in round 1, parity-tested and timed on B200
+// in round 2: clean, but SLOWER on the layers that use this kernel (layer2 3x3: 0.081-0.093 ms against 0.072-0.084 ms), so it
+// was removed; profiles/README.md has the numbers and tools/tma_mcast_test.cu the probe.)
+template <typename T, int BLOCK_N, int STAGES, int A_MODE>
 __global__ void __launch_bounds__(CONV_TC_THREADS)
 conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int n_tiles)
 {
     static_assert(GATHER_LAG <= STAGES - 1, "producer lag must leave one free stage");
-    static_assert(!MCAST || ((A_MODE == A_TILED || A_MODE == A_IM2COL) && BLOCK_N >= 64), "multicast variant is TMA-fed");
     using L = ConvTcSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     constexpr bool EPI_TMA_CAPABLE = BLOCK_N >= 64;
@@ -96,11 +95,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // MCAST: consecutive block pairs form the clusters; both CTAs of a cluster share the n tile
-    const uint32_t crank = MCAST ? cluster_ctarank() : 0u;
-    const int tile_id = MCAST ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_id = static_cast<int>(blockIdx.x);
     const int n_tile = tile_id % n_tiles;
-    const int m_tile = MCAST ? (tile_id / n_tiles) * 2 + static_cast<int>(crank) : tile_id / n_tiles;
+    const int m_tile = tile_id / n_tiles;
     const int n0 = n_tile * BLOCK_N;
     const int num_kb = (p.K + TILE_K - 1) / TILE_K;
 
@@ -108,7 +105,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + s * 8, (A_MODE == A_GATHER || A_MODE == A_STEM) ? 5 : 1);   // 4 gather warps + the TMA thread
-            mbar_init(bar_empty + s * 8, MCAST ? 2 : 1);                                      // MCAST: released by both CTAs' MMAs
+            mbar_init(bar_empty + s * 8, 1);
         }
         mbar_init(bar_tmem, 1);
         mbar_init(bar_res, 1);
@@ -130,7 +127,6 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (MCAST) cluster_sync_all();                      // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_ptr_s;
 
@@ -142,7 +138,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
         const bool row_ok = r < p.M;
         // ---------------- optional second TMA producer (experiment, ConvParams::split_producer): warp 6 issues the weight tiles
         // while warp 4 issues A; its epilogue share starts afterwards (every load is issued long before the last MMA retires)
-        if constexpr ((A_MODE == A_TILED || A_MODE == A_IM2COL) && !MCAST) {
+        if constexpr (A_MODE == A_TILED || A_MODE == A_IM2COL) {
             if (p.split_producer && warp == 6) {
                 if (lane == 0) {
                     for (int kb = 0; kb < num_kb; ++kb) {
@@ -353,10 +349,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
                 const int it = kb / STAGES;
                 mbar_wait(bar_empty + s * 8, (it & 1) ^ 1);
                 mbar_arrive_expect_tx(bar_full + s * 8, tx_bytes);
-                if constexpr (MCAST) {                            // our half of the weight tile, delivered to both CTAs
-                    tma_load_2d_mcast(b_base + s * L::B_STAGE_BYTES + crank * (L::B_STAGE_BYTES / 2), &maps.b, bar_full + s * 8,
-                                      kb * TILE_K, n0 + static_cast<int>(crank) * (BLOCK_N / 2), static_cast<uint16_t>(3));
-                } else if (!(p.split_producer && (A_MODE == A_TILED || A_MODE == A_IM2COL)))
+                if (!(p.split_producer && (A_MODE == A_TILED || A_MODE == A_IM2COL)))
                     tma_load_2d(b_base + s * L::B_STAGE_BYTES, &maps.b, bar_full + s * 8, kb * TILE_K, n0);
                 if constexpr (A_MODE == A_TILED) {
                     tma_load_2d(a_base + s * A_STAGE_BYTES, &maps.a, bar_full + s * 8, kb * TILE_K, m_tile * TILE_M);
@@ -387,8 +380,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
                     umma_f16(tmem_acc, umma_desc_sw128(a_s + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
                              static_cast<uint32_t>((kb | k) != 0));
                 }
-                if constexpr (MCAST) umma_commit_mcast(bar_empty + s * 8, static_cast<uint16_t>(3));   // release in BOTH CTAs
-                else umma_commit(bar_empty + s * 8);              // frees the smem stage when these MMAs retire
+                umma_commit(bar_empty + s * 8);                   // frees the smem stage when these MMAs retire
             }
             umma_commit(bar_tmem);                                // accumulator complete
         }
@@ -398,7 +390,6 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     // ---------------- teardown
     tc_fence_before();
     __syncthreads();
-    if constexpr (MCAST) cluster_sync_all();                      // the peer may still signal our empty barriers
     if (warp == 4) {
         tc_fence_after();
         tmem_dealloc(tmem_acc, TMEM_COLS);
@@ -863,35 +854,6 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
                 if (g_use_2cta && m_tiles >= 2) return launch_pair<T, 256, 4>(p, maps, w, mode, m_tiles, n_tiles, s);
             }
             return launch_persistent<T, BLOCK_N, (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6))>(p, maps, mode, m_tiles, n_tiles, s);
-        }
-    }
-    if constexpr (BLOCK_N == 64 || BLOCK_N == 128) {
-        // experiment (SPECB200_MCAST_B=1): clusters of two one-tile CTAs share the weight tile by TMA multicast
-        static int mcast = -1;
-        if (mcast < 0) { const char* e = getenv("SPECB200_MCAST_B"); mcast = (e && e[0] == '1') ? 1 : 0; }
-        if (mcast && (mode == A_TILED || mode == A_IM2COL) && m_tiles >= 2) {
-            if (!make_tmap_2d(&maps.b, w.w_tc, static_cast<uint64_t>(w.cout_pad), static_cast<uint64_t>(w.K_pad), static_cast<uint64_t>(w.K_pad), BLOCK_N / 2)) return false;
-            auto m0 = conv_tc_kernel<T, BLOCK_N, STAGES, A_TILED, true>;
-            auto m1 = conv_tc_kernel<T, BLOCK_N, STAGES, A_IM2COL, true>;
-            static DeviceOnce attr_m;
-            if (attr_m.need()) {
-                if (!check_cuda(cudaFuncSetAttribute(m0, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
-                if (!check_cuda(cudaFuncSetAttribute(m1, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES), "smem attr")) return false;
-            }
-            const long long gridm = 2LL * ((m_tiles + 1) / 2) * n_tiles;
-            if (gridm > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return false; }
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(static_cast<unsigned>(gridm));
-            cfg.blockDim = dim3(CONV_TC_THREADS);
-            cfg.dynamicSmemBytes = L::DYN_BYTES;
-            cfg.stream = s;
-            cudaLaunchAttribute at;
-            at.id = cudaLaunchAttributeClusterDimension;
-            at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-            cfg.attrs = &at;
-            cfg.numAttrs = 1;
-            const cudaError_t e = (mode == A_TILED) ? cudaLaunchKernelEx(&cfg, m0, p, maps, n_tiles) : cudaLaunchKernelEx(&cfg, m1, p, maps, n_tiles);
-            return check_cuda(e, "conv_tc (multicast) launch");
         }
     }
     auto k0 = conv_tc_kernel<T, BLOCK_N, STAGES, A_TILED>;
