@@ -94,6 +94,8 @@ int32_t specb200_trunk_num_ops(specb200_trunk_t* t);
 /* number of [downsample] conv1x1-conv3x3-conv1x1 bottleneck groups of the program that run as ONE fused launch
  * (64 mid channels, 256 outputs, stride 1: ResNet-50 / HRNet layer1; 16-bit modes only) */
 int32_t specb200_trunk_num_fused_bottlenecks(specb200_trunk_t* t);
+/* index of the first op of the fused group program op `op` belongs to, -1 if it runs on its own */
+int32_t specb200_trunk_fused_group_first_op(specb200_trunk_t* t, int32_t op);
 /* Diagnostic variant of specb200_trunk_forward: brackets every op with CUDA events on `stream`, SYNCHRONISES, and
  * writes per-op device milliseconds to op_ms_host[0 .. n_ops+1] (0 = image NCHW->NHWC conversion, 1..n_ops = ops in
  * program order, n_ops+1 = average pool), summed over batch chunks.  Used by bench.py for the live roofline. */

@@ -61,6 +61,7 @@ _PROTOS = {
     'specb200_trunk_last_launches': (C.c_int64, [C.c_void_p]),
     'specb200_trunk_num_ops': (C.c_int32, [C.c_void_p]),
     'specb200_trunk_num_fused_bottlenecks': (C.c_int32, [C.c_void_p]),
+    'specb200_trunk_fused_group_first_op': (C.c_int32, [C.c_void_p, C.c_int32]),
     'specb200_trunk_profile': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'specb200_trunk_destroy': (None, [C.c_void_p]),

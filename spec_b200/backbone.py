@@ -421,9 +421,11 @@ class Trunk(nn.Module):
                 self.n_output_channels, ms.ctypes.data, torch.cuda.current_stream(images.device).cuda_stream))
         es = 4 if self.precision == 'fp32' else 2
         shapes = {0: (H, W)}
+        shapes_in = {}
         rows = [dict(name='images_to_nhwc', type=0, ms=float(ms[0]), flops=0, bytes=B * H * W * (12 + es * 4))]
         for i, o in enumerate(self._program.ops):
             sh = shapes[o['src']]
+            shapes_in[i] = sh
             r = dict(type=o['type'], ms=float(ms[i + 1]), flops=0)
             if o['type'] == OP_CONV:
                 ho = (sh[0] + 2 * o['pad'] - o['kh']) // o['stride'] + 1
@@ -449,6 +451,26 @@ class Trunk(nn.Module):
                 d = shapes[o['dst']]
                 r.update(name='upadd', bytes=es * B * self._program.buf_ch[o['dst']] * (2 * d[0] * d[1] + sh[0] * sh[1]))
             rows.append(r)
+        # fused bottleneck groups run as ONE launch: the time is on the group's first op; its algorithmic bytes are the block's
+        # input + output (+ weights), the 64-channel intermediates never reach HBM
+        L = _lib.lib()
+        groups = {}
+        for i in range(n):
+            g = int(L.specb200_trunk_fused_group_first_op(self._handle, i)) if self.precision != 'fp32' else -1
+            if g >= 0:
+                groups.setdefault(g, []).append(i)
+        for g, members in groups.items():
+            rs = [rows[1 + i] for i in members]
+            first, last = rs[0], rs[-1]
+            w_bytes = sum(es * r['cout'] * r['cin'] * r['k'] * r['k'] for r in rs)
+            hw = B * shapes_in[members[0]][0] * shapes_in[members[0]][1]
+            first_cin = rows[1 + members[0]]['cin']
+            total = es * hw * (first_cin + last['cout']) + w_bytes
+            for r in rs:
+                r['bytes'] = 0
+                r['fused_into'] = first['name']
+            first['bytes'] = total
+            first['name'] = first['name'] + ' [fused block x%d]' % len(members)
         rows.append(dict(name='avgpool', type=0, ms=float(ms[n + 1]), flops=0, bytes=0))
         return rows
 

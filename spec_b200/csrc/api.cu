@@ -495,6 +495,10 @@ extern "C" int64_t specb200_trunk_last_launches(specb200_trunk_t* t) { return t 
 
 extern "C" int32_t specb200_trunk_num_ops(specb200_trunk_t* t) { return t ? static_cast<int32_t>(t->ops.size()) : 0; }
 extern "C" int32_t specb200_trunk_num_fused_bottlenecks(specb200_trunk_t* t) { return t ? static_cast<int32_t>(t->groups.size()) : 0; }
+extern "C" int32_t specb200_trunk_fused_group_first_op(specb200_trunk_t* t, int32_t op) {
+    if (!t || op < 0 || op >= static_cast<int32_t>(t->op_group.size()) || t->op_group[op] < 0) return -1;
+    return t->groups[t->op_group[op]].first;
+}
 
 extern "C" int specb200_trunk_profile(specb200_trunk_t* t, const float* images, int32_t batch, int32_t h, int32_t w,
                                       void* workspace, int64_t workspace_bytes, float* pooled_out, int32_t pooled_ld,
@@ -781,8 +785,9 @@ extern "C" int specb200_hmrtail_forward(specb200_hmrtail_t* t, int32_t B, void* 
     const int C = t->C, ldx = t->ldx;
     int64_t n = 0;
     // G = xf (D W2 W1[:, :C])^T + c0 : the only GEMM of the folded head
-    if (!linear_f32_launch(w.X, ldx, t->Fx, C, t->c0, nullptr, 0, w.G, 160, B, 157, C, s, HEAD_KSPLIT, static_cast<size_t>(B) * 160)) return 1; ++n;
-    if (!head_iter_launch(w.X, ldx, C, w.G, HEAD_KSPLIT, t->AsT, t->init157, cam_rotmat, cam_intr, img_h, t->use_cam_feats, B, s)) return 1; ++n;
+    int ks_used = HEAD_KSPLIT;                                // e.g. C = 100 yields 7 slices, not 8: sum what was written
+    if (!linear_f32_launch(w.X, ldx, t->Fx, C, t->c0, nullptr, 0, w.G, 160, B, 157, C, s, HEAD_KSPLIT, static_cast<size_t>(B) * 160, &ks_used)) return 1; ++n;
+    if (!head_iter_launch(w.X, ldx, C, w.G, ks_used, t->AsT, t->init157, cam_rotmat, cam_intr, img_h, t->use_cam_feats, B, s)) return 1; ++n;
     if (!smpl_prep_launch(w.X, ldx, C, t->Jt, t->Js, w.pf, w.A, w.Jp, o->pred_pose, o->ld_pose, o->pred_pose_6d, o->ld_pose_6d,
                           o->pred_shape, o->ld_shape, o->pred_cam, o->ld_cam, B, s)) return 1; ++n;
     if (!smpl_verts_launch(t->Vt, t->Sd, t->Pd, t->Wl, t->Jx, w.X, ldx, C, w.pf, w.A, o->smpl_vertices, o->ld_vertices, w.part, B, s)) return 1; ++n;

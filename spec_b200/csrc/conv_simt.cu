@@ -193,7 +193,7 @@ linear_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict_
 
 bool linear_f32_launch(const float* A, int lda, const float* W, int ldw, const float* bias, const float* add,
                        int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s, int ksplit,
-                       size_t split_stride) {
+                       size_t split_stride, int* ksplit_used) {
     if ((K % 4) != 0 || (lda % 4) != 0 || (ldw % 4) != 0 ||
         (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(W) & 15) != 0) {
         set_error("linear_f32: K, lda, ldw must be multiples of 4 and pointers 16-byte aligned");
@@ -202,7 +202,8 @@ bool linear_f32_launch(const float* A, int lda, const float* W, int ldw, const f
     if (ksplit < 1) ksplit = 1;
     int k_chunk = (K + ksplit - 1) / ksplit;
     k_chunk = (k_chunk + 3) / 4 * 4;
-    ksplit = (K + k_chunk - 1) / k_chunk;
+    ksplit = (K + k_chunk - 1) / k_chunk;                    // rounding k_chunk up to a multiple of 4 can leave fewer slices than asked for
+    if (ksplit_used) *ksplit_used = ksplit;
     dim3 grid((N + LN_BN - 1) / LN_BN, (M + LN_BM - 1) / LN_BM, ksplit);
     linear_f32_kernel<<<grid, 256, 0, s>>>(A, lda, W, ldw, bias, add, add_ld, out, out_ld, M, N, K, k_chunk, split_stride);
     return check_cuda(cudaGetLastError(), "linear_f32 launch");

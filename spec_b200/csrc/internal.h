@@ -98,10 +98,11 @@ bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N,
 // fp32 SIMT implicit-GEMM conv and linear (conv_simt.cu).
 bool conv_f32_launch(const ConvParams& p, const ConvWeights& w, cudaStream_t s);
 // out[M, n0:n0+N] (ld out_ld) = A[M,K](ld lda) @ W[N,K]^T (ld ldw) + bias[N] + add[M,N](ld add_ld) ; fp32
-// ksplit > 1: split-K partial sums, slice z written to out + z*split_stride (consumer adds them in order)
+// ksplit > 1: split-K partial sums, slice z written to out + z*split_stride (consumer adds them in order); the number of slices
+// actually written is returned in *ksplit_used (<= ksplit) -- the consumer must sum exactly that many
 bool linear_f32_launch(const float* A, int lda, const float* W, int ldw, const float* bias, const float* add,
                        int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s, int ksplit = 1,
-                       size_t split_stride = 0);
+                       size_t split_stride = 0, int* ksplit_used = nullptr);
 
 // eval-side metrics (eval.cu)
 bool eval_launch(const float* JT, const int* map14, int B, const float* pred_verts, long long ld_pred, const float* gt_kp14,

@@ -74,7 +74,8 @@ for i, r in enumerate(rows[2:]):
         pass
 if tens:
     tt = sum(t for t, _, _ in tens)
-    total_bytes = sum(b for _, _, b in tens)
+    unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(rows[1][col['dram__bytes_read.sum']], 1e6)
+    total_bytes = sum(b for _, _, b in tens) * unit          # the raw page states one unit per column (row 2 of the CSV)
     out.append(f'\ntime-weighted tensor-pipe utilisation over these launches: **{sum(t*p for t,p,_ in tens)/tt:.1f}%**; '
                f'DRAM traffic {total_bytes/1e9:.2f} GB per step over {len(tens)} conv-family launches\n')
     # bench.py reads roofline.traffic from this file (key = backbone|batch|precision of the captured command)
