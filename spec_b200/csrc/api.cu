@@ -434,9 +434,14 @@ static int trunk_forward_impl(specb200_trunk_t* t, const float* images, int32_t 
                     if (!ok) return 1;
                     break;
                 }
-                case SPECB200_OP_MAXPOOL:
-                    if (!maxpool3x3s2_launch(buf[o.src], buf[o.dst], nb, sS.H, sS.W, t->buf_ch[o.src], dS.H, dS.W, t->prec, s)) return 1;
+                case SPECB200_OP_MAXPOOL: {
+                    // is the pooled tensor the output of a conv + ReLU (>= 0)?  the last writer of o.src before this op decides
+                    bool nonneg = false;
+                    for (int j = static_cast<int>(i) - 1; j >= 0; --j)
+                        if (t->ops[j].dst == o.src) { nonneg = t->ops[j].type == SPECB200_OP_CONV && t->ops[j].relu != 0 && t->ops[j].dst_coff == 0; break; }
+                    if (!maxpool3x3s2_launch(buf[o.src], buf[o.dst], nb, sS.H, sS.W, t->buf_ch[o.src], dS.H, dS.W, t->prec, s, nonneg)) return 1;
                     break;
+                }
                 case SPECB200_OP_UPADD:
                     if (!upsample_add_launch(buf[o.src], buf[o.dst], nb, dS.H, dS.W, t->buf_ch[o.dst], o.shift, o.relu, t->prec, s)) return 1;
                     break;

@@ -103,7 +103,115 @@ __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, in
 
 // (Two horizontally adjacent outputs per thread -- a 3x5 window read once, 15 loads for two outputs instead of 18 -- was
 // also measured SLOWER, 0.162 vs 0.139 ms: half the threads, less latency hiding.)
-bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int prec, cudaStream_t s) {
+// TMA-tiled variant for the ResNet stem (C = 64, 16-bit, NON-NEGATIVE input = the output of a conv + ReLU): the kernel above re-reads
+// every input pixel up to nine times through L1 (0.137 ms at B=256 = 0.56 of the HBM roofline).  Here a persistent CTA per SM
+// pulls the 17 x 33-pixel input patch of an 8 x 16 output tile into shared memory with ONE 4-D TMA box (72 KB, 128B-swizzled rows
+// of 64 channels; out-of-image pixels are zero-filled, which equals max-pool's -inf padding BECAUSE the values are >= 0 and every
+// window holds a real pixel), double-buffered one tile ahead; 256 threads take the 3x3 maxima from shared memory (16-byte chunk
+// per thread: eight threads per pixel, conflict-free) into a swizzled staging tile that leaves through one TMA store.
+constexpr int MP_TH = 8, MP_TW = 16;
+constexpr int MP_PH = 2 * MP_TH + 1, MP_PW = 2 * MP_TW + 1;          // 17 x 33 input pixels
+constexpr int MP_PATCH_TX = MP_PH * MP_PW * 128;                     // 71808
+constexpr int MP_PATCH_BYTES = (MP_PATCH_TX + 1023) / 1024 * 1024;   // 72704
+constexpr int MP_ST_BYTES = MP_TH * MP_TW * 128;                     // 16384
+constexpr int MP_DYN_BYTES = 2 * MP_PATCH_BYTES + 2 * MP_ST_BYTES + 64 + 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+maxpool_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out, int tiles_w, int tiles_h,
+                   int total_tiles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t patch_s = sbase, st_s = sbase + 2 * MP_PATCH_BYTES, bar_full = st_s + 2 * MP_ST_BYTES;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar_full, 1); mbar_init(bar_full + 8, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap_in); tma_prefetch_desc(&tmap_out);
+    }
+    __syncthreads();
+    auto issue = [&](int tile, uint32_t b) {
+        const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+        mbar_arrive_expect_tx(bar_full + b * 8, MP_PATCH_TX);
+        tma_load_4d(patch_s + b * MP_PATCH_BYTES, &tmap_in, bar_full + b * 8, 0, 2 * tw * MP_TW - 1, 2 * th * MP_TH - 1, n);
+    };
+    if (tid == 0 && static_cast<int>(blockIdx.x) < total_tiles) issue(blockIdx.x, 0);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t b = it & 1, ph = (it >> 1) & 1;
+        if (tid == 0) {
+            if (tile + static_cast<int>(gridDim.x) < total_tiles) issue(tile + gridDim.x, b ^ 1);   // buffer b^1 was released by the barrier below
+            tma_store_wait_read<1>();                                   // the store of tile it-2 has read staging[b]
+        }
+        mbar_wait(bar_full + b * 8, ph);
+        __syncthreads();                                                // staging[b] is free for everybody
+        const uint32_t patch = patch_s + b * MP_PATCH_BYTES, st = st_s + b * MP_ST_BYTES;
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep) {
+            const int item = tid + rep * 256;
+            const int p = item >> 3, k = item & 7;                      // output pixel of the tile, 16-byte channel chunk
+            const int pr = p >> 4, pc = p & 15;
+            uint32_t m[4] = {0u, 0u, 0u, 0u};                           // +0.0: the identity for non-negative inputs
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const uint32_t R = static_cast<uint32_t>((2 * pr + dy) * MP_PW + 2 * pc + dx);
+                    uint32_t v[4];
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                                 : "r"(patch + R * 128u + ((static_cast<uint32_t>(k) ^ (R & 7u)) << 4)));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if constexpr (sizeof(T) == 2 && DT<T>::umma_fmt == 1) {
+                            __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m[e]), *reinterpret_cast<__nv_bfloat162*>(&v[e]));
+                            m[e] = *reinterpret_cast<uint32_t*>(&r2);
+                        } else {
+                            __half2 r2 = __hmax2(*reinterpret_cast<__half2*>(&m[e]), *reinterpret_cast<__half2*>(&v[e]));
+                            m[e] = *reinterpret_cast<uint32_t*>(&r2);
+                        }
+                    }
+                }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(st + static_cast<uint32_t>(p) * 128u + ((static_cast<uint32_t>(k) ^ (static_cast<uint32_t>(p) & 7u)) << 4)),
+                         "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncthreads();                                                // staging[b] complete; patch[b] no longer read
+        if (tid == 0) {
+            const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+            tma_store_4d(&tmap_out, st, 0, tw * MP_TW, th * MP_TH, n);
+            tma_store_commit();
+        }
+    }
+    if (tid == 0) tma_store_wait_read0();
+}
+
+bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int prec, cudaStream_t s, bool nonneg_input) {
+    static int no_tma = -1;                                              // SPECB200_NO_POOL_TMA=1: the L1 re-read kernel (A/B baseline)
+    if (no_tma < 0) { const char* e = getenv("SPECB200_NO_POOL_TMA"); no_tma = (e && e[0] == '1') ? 1 : 0; }
+    if (!no_tma && nonneg_input && C == 64 && prec != PREC_F32 && H >= MP_PH && W >= MP_PW) {
+        CUtensorMap tin, tout;
+        if (!make_tmap_nhwc(&tin, in, 64, W, H, N, MP_PW, MP_PH)) return false;
+        if (!make_tmap_nhwc(&tout, out, 64, Wo, Ho, N, MP_TW, MP_TH)) return false;
+        static DeviceOnce attr;
+        if (attr.need()) {
+            if (!check_cuda(cudaFuncSetAttribute(maxpool_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_DYN_BYTES), "maxpool attr")) return false;
+            if (!check_cuda(cudaFuncSetAttribute(maxpool_tma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_DYN_BYTES), "maxpool attr")) return false;
+        }
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!check_cuda(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev), "sm count")) return false;
+        }
+        const int tiles_w = (Wo + MP_TW - 1) / MP_TW, tiles_h = (Ho + MP_TH - 1) / MP_TH;
+        const long long total = static_cast<long long>(N) * tiles_w * tiles_h;
+        if (total > 0x7fffffffLL) { set_error("maxpool: too many tiles"); return false; }
+        const unsigned grid = static_cast<unsigned>(total < num_sms ? total : num_sms);
+        if (prec == PREC_BF16) maxpool_tma_kernel<__nv_bfloat16><<<grid, 256, MP_DYN_BYTES, s>>>(tin, tout, tiles_w, tiles_h, static_cast<int>(total));
+        else maxpool_tma_kernel<__half><<<grid, 256, MP_DYN_BYTES, s>>>(tin, tout, tiles_w, tiles_h, static_cast<int>(total));
+        return check_cuda(cudaGetLastError(), "maxpool (tma)");
+    }
     SB_DISPATCH_PREC(prec, {
         const long long total = static_cast<long long>(N) * Ho * Wo * (C / V16<T>::N);
         maxpool_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, Ho, Wo);

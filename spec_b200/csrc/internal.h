@@ -111,7 +111,9 @@ bool eval_launch(const float* JT, const int* map14, int B, const float* pred_ver
 
 // elementwise / layout kernels (elementwise.cu)
 bool images_to_nhwc_launch(const float* img_nchw, void* out_nhwc, int N, int H, int W, int cpad, int prec, cudaStream_t s);
-bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int prec, cudaStream_t s);
+// nonneg_input: the source tensor is the output of a conv + ReLU (enables the TMA-tiled kernel, whose zero-filled borders act as padding)
+bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int prec, cudaStream_t s,
+                         bool nonneg_input = false);
 bool upsample_add_launch(const void* lo, void* acc, int N, int Ho, int Wo, int C, int shift, int relu, int prec, cudaStream_t s);
 bool bilinear_launch(const void* in, void* out, int N, int H, int W, int C, int Ho, int Wo, int out_ld, int out_coff,
                      int prec, cudaStream_t s);
