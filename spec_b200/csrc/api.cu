@@ -750,7 +750,7 @@ extern "C" int specb200_hmrtail_create(specb200_hmrtail_t** out, const specb200_
 
 namespace {
 constexpr int HEAD_KSPLIT = 8;     // split-K slices of the G GEMM (N = 157 alone would fill only 24 CTAs)
-struct HmrWs { float *X, *G, *pf, *A, *Jp, *part; size_t total; };
+struct HmrWs { float *X, *G, *pf, *A, *Jp; size_t total; };
 HmrWs hmr_carve(const specb200_hmrtail* t, int B, void* base) {
     HmrWs w;
     size_t off = 0;
@@ -760,7 +760,6 @@ HmrWs hmr_carve(const specb200_hmrtail* t, int B, void* base) {
     w.pf = take(static_cast<size_t>(B) * PF_LD);
     w.A = take(static_cast<size_t>(B) * 288);
     w.Jp = take(static_cast<size_t>(B) * 72);
-    w.part = take(static_cast<size_t>(B) * SMPL_NVT * 27);
     w.total = off;
     return w;
 }
@@ -795,8 +794,8 @@ extern "C" int specb200_hmrtail_forward(specb200_hmrtail_t* t, int32_t B, void* 
     if (!head_iter_launch(w.X, ldx, C, w.G, ks_used, t->AsT, t->init157, cam_rotmat, cam_intr, img_h, t->use_cam_feats, B, s)) return 1; ++n;
     if (!smpl_prep_launch(w.X, ldx, C, t->Jt, t->Js, w.pf, w.A, w.Jp, o->pred_pose, o->ld_pose, o->pred_pose_6d, o->ld_pose_6d,
                           o->pred_shape, o->ld_shape, o->pred_cam, o->ld_cam, B, s)) return 1; ++n;
-    if (!smpl_verts_launch(t->Vt, t->Sd, t->Pd, t->Wl, t->Jx, w.X, ldx, C, w.pf, w.A, o->smpl_vertices, o->ld_vertices, w.part, B, s)) return 1; ++n;
-    if (!smpl_joints_launch(o->smpl_vertices, o->ld_vertices, w.Jp, w.part, w.X, ldx, C, cam_rotmat, cam_intr, bbox_scale, bbox_center,
+    if (!smpl_verts_launch(t->Vt, t->Sd, t->Pd, t->Wl, w.X, ldx, C, w.pf, w.A, o->smpl_vertices, o->ld_vertices, B, s)) return 1; ++n;
+    if (!smpl_joints_launch(o->smpl_vertices, o->ld_vertices, w.Jp, t->Jx, w.X, ldx, C, cam_rotmat, cam_intr, bbox_scale, bbox_center,
                             img_w, img_h, o->smpl_joints3d, o->ld_joints3d, o->smpl_joints2d, o->ld_joints2d, o->pred_cam_t, o->ld_cam_t,
                             t->use_cam, t->focal, t->img_res, B, s)) return 1; ++n;
     t->last_launches = n;

@@ -244,22 +244,30 @@ bool smpl_prep_launch(const float* X, int ldx, int C, const float* Jt, const flo
 }
 
 // ------------------------------------------------------------------ SMPL vertices
-// Tile: 64 vertices x 32 images per CTA; 256 threads: lane -> the adjacent vertices (2*lane, 2*lane+1), warp -> 4 images.
-// (Adjacent vertices + a transposed pose-feature chunk turn the 10 scalar shared-memory loads per k of the pose-blend loop --
-// it was LDS-bound: 10 LDS per 24 FFMA -- into one LDS.128 and three LDS.64.)
-constexpr int SV_TV = 64, SV_TB = 32, SV_BK = 16;
+// Tile: 64 vertices x 64 images per CTA; 256 threads: lane -> the adjacent vertices (2*lane, 2*lane+1), warp -> 8 images.
+//
+// v_posed = v_template + shapedirs . beta + posedirs . pose_feature is ONE k-loop over 14 chunks of 16 "features": chunks
+// 0..12 are the 207 pose features, chunk 13 holds the 10 betas and a constant 1 against shapedirs / v_template (added last:
+// the small pose offsets are summed before the O(1) template is added).  Per k a warp issues 2 LDS.128 (8 image features,
+// broadcast) + 3 LDS.64 (3 coordinates x 2 vertices) for 48 FFMA; the round-1 shape (4 images per warp: 4 LDS per 24 FFMA,
+// 7 shared-memory wavefronts per 24 FFMA) was bound by the shared-memory pipe, not by the FP32 pipe.  The next chunk is
+// fetched into registers while the current one is consumed.  Skinning is applied as out = sum_j w_j (A_j [v;1]) -- the same
+// 12 FFMA per (joint, vertex) as building T = sum_j w_j A_j first, but 6 accumulators instead of 24, and A_j is read once for
+// the thread's two vertices (5 wavefronts per 24 FFMA).  The extra-joint regression moved to smpl_joints_kernel (it cost
+// 540 shuffles per thread here).  Vertices leave through a per-warp shared-memory transpose as full 128-byte rows.
+constexpr int SV_TV = 64, SV_TB = 64, SV_BK = 16, SV_NCH = 14;
 struct SvSmem {
-    float A[SV_TB][24][12];          // skinning transforms of the tile's images (36 KB)
-    float P[SV_BK][3][SV_TV];        // posedirs chunk (12 KB)
-    float pf[SV_BK][SV_TB];          // pose-feature chunk, [k][image]
-    float beta[SV_TB][10];
+    float A[SV_TB][24][12];          // skinning transforms of the tile's images (72 KB)
+    float P[SV_BK][3][SV_TV];        // basis chunk (12 KB); reused as the output transpose buffer
+    float pf[SV_BK][SV_TB];          // feature chunk, [k][image]
+    float W[24][SV_TV];              // skinning weights of the tile's vertices
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 smpl_verts_kernel(const float* __restrict__ Vt, const float* __restrict__ Sd, const float* __restrict__ Pd,
-                  const float* __restrict__ Wl, const float* __restrict__ Jx, const float* __restrict__ X, int ldx, int C,
+                  const float* __restrict__ Wl, const float* __restrict__ X, int ldx, int C,
                   const float* __restrict__ pf, const float* __restrict__ Amat, float* __restrict__ o_verts,
-                  long long ld_verts, float* __restrict__ partials /*[B][NVT][27]*/, int B)
+                  long long ld_verts, int B)
 {
     extern __shared__ __align__(16) uint8_t sv_raw[];
     SvSmem& sm = *reinterpret_cast<SvSmem*>(sv_raw);
@@ -267,155 +275,157 @@ smpl_verts_kernel(const float* __restrict__ Vt, const float* __restrict__ Sd, co
     const int v0 = blockIdx.x * SV_TV;
     const int b0 = blockIdx.y * SV_TB;
 
-    // stage per-image data
-    for (int i = tid; i < SV_TB * 288; i += 256) {
-        const int bi = i / 288, e = i - bi * 288;
-        reinterpret_cast<float*>(sm.A)[i] = (b0 + bi < B) ? Amat[static_cast<size_t>(b0 + bi) * 288 + e] : 0.f;
+    // stage per-image transforms and per-vertex weights
+    for (int i = tid; i < SV_TB * 72; i += 256) {
+        const int bi = i / 72;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + bi < B) v = reinterpret_cast<const float4*>(Amat + static_cast<size_t>(b0) * 288)[i];
+        reinterpret_cast<float4*>(sm.A)[i] = v;
     }
-    for (int i = tid; i < SV_TB * 10; i += 256) {
-        const int bi = i / 10, l = i - bi * 10;
-        sm.beta[bi][l] = (b0 + bi < B) ? X[static_cast<size_t>(b0 + bi) * ldx + C + 144 + l] : 0.f;
+    for (int i = tid; i < 24 * (SV_TV / 4); i += 256) {
+        const int j = i / (SV_TV / 4), vq = (i - j * (SV_TV / 4)) * 4;
+        *reinterpret_cast<float4*>(&sm.W[j][vq]) = *reinterpret_cast<const float4*>(Wl + static_cast<size_t>(j) * SMPL_VP + v0 + vq);
     }
 
-    float acc[4][2][3];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) acc[i][h][c] = 0.f;
-
-    // pose blendshapes: acc[img][vert][coord] = sum_p pf[img][p] * Pd[p][coord][vert]
-    for (int k0 = 0; k0 < PF_LD; k0 += SV_BK) {
-        __syncthreads();
+    float4 rp[3], rf;                                           // the chunk in flight: 3 basis float4 + 4 features of one image
+    const int f_bi = tid >> 2, f_kq = (tid & 3) * 4;
+    auto fetch = [&](int ch) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const int idx = tid + q * 256;                     // 768 float4 = 16 x 3 x 64 floats
             const int kk = idx / 48, rem = idx - kk * 48;
             const int c = rem / 16, vq = (rem - c * 16) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k0 + kk < 207)
-                v = *reinterpret_cast<const float4*>(Pd + (static_cast<size_t>(k0 + kk) * 3 + c) * SMPL_VP + v0 + vq);
-            *reinterpret_cast<float4*>(&sm.P[kk][c][vq]) = v;
-        }
-        if (tid < 128) {
-            const int bi = tid >> 2, kq = (tid & 3) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b0 + bi < B) v = *reinterpret_cast<const float4*>(pf + static_cast<size_t>(b0 + bi) * PF_LD + k0 + kq);
-            sm.pf[kq + 0][bi] = v.x; sm.pf[kq + 1][bi] = v.y; sm.pf[kq + 2][bi] = v.z; sm.pf[kq + 3][bi] = v.w;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < SV_BK; ++kk) {
-            float p[3][2];
-            const float4 a4 = *reinterpret_cast<const float4*>(&sm.pf[kk][warp * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float2 p2 = *reinterpret_cast<const float2*>(&sm.P[kk][c][2 * lane]);
-                p[c][0] = p2.x; p[c][1] = p2.y;
+            const float* src = nullptr;
+            if (ch < SV_NCH - 1) {
+                const int k = ch * SV_BK + kk;
+                if (k < 207) src = Pd + (static_cast<size_t>(k) * 3 + c) * SMPL_VP;
+            } else if (kk < 10) {
+                src = Sd + (static_cast<size_t>(kk) * 3 + c) * SMPL_VP;
+            } else if (kk == 10) {
+                src = Vt + static_cast<size_t>(c) * SMPL_VP;
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) acc[i][h][c] = fmaf(a[i], p[c][h], acc[i][h][c]);
+            rp[q] = src ? *reinterpret_cast<const float4*>(src + v0 + vq) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        rf = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int b = b0 + f_bi;
+        if (b < B) {
+            if (ch < SV_NCH - 1) {
+                rf = *reinterpret_cast<const float4*>(pf + static_cast<size_t>(b) * PF_LD + ch * SV_BK + f_kq);
+            } else {
+                const float* beta = X + static_cast<size_t>(b) * ldx + C + 144;
+                float e[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const int k = f_kq + i; e[i] = k < 10 ? beta[k] : (k == 10 ? 1.f : 0.f); }
+                rf = make_float4(e[0], e[1], e[2], e[3]);
+            }
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int idx = tid + q * 256;
+            const int kk = idx / 48, rem = idx - kk * 48;
+            const int c = rem / 16, vq = (rem - c * 16) * 4;
+            *reinterpret_cast<float4*>(&sm.P[kk][c][vq]) = rp[q];
+        }
+        sm.pf[f_kq + 0][f_bi] = rf.x; sm.pf[f_kq + 1][f_bi] = rf.y; sm.pf[f_kq + 2][f_bi] = rf.z; sm.pf[f_kq + 3][f_bi] = rf.w;
+    };
+
+    float acc[8][2][3];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[i][h][c] = 0.f;
+
+    const bool live = b0 + warp * 8 < B;                        // warps whose 8 images are all past the batch only help staging
+    fetch(0);
+    stash();
+    for (int ch = 0; ch < SV_NCH; ++ch) {
+        __syncthreads();                                        // chunk ch is in shared memory
+        if (ch + 1 < SV_NCH) fetch(ch + 1);
+        if (live) {
+#pragma unroll
+            for (int kk = 0; kk < SV_BK; ++kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&sm.pf[kk][warp * 8]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&sm.pf[kk][warp * 8 + 4]);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float p[3][2];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float2 p2 = *reinterpret_cast<const float2*>(&sm.P[kk][c][2 * lane]);
+                    p[c][0] = p2.x; p[c][1] = p2.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) acc[i][h][c] = fmaf(a[i], p[c][h], acc[i][h][c]);
+            }
+        }
+        __syncthreads();                                        // everyone is done reading chunk ch
+        if (ch + 1 < SV_NCH) stash();
     }
+    if (!live) return;
 
-    float ej[4][27];                                            // extra-joint partial sums of this thread
+    // skinning + store, one image at a time; sm.P is free now: 192 floats per warp for the output transpose
+    float* tr = &sm.P[0][0][0] + warp * 192;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int q = 0; q < 27; ++q) ej[i][q] = 0.f;
-
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int v = v0 + 2 * lane + h;
-        // shape blendshapes
-        float vs[4][3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float t = Vt[static_cast<size_t>(c) * SMPL_VP + v];
-            float s[10];
-#pragma unroll
-            for (int l = 0; l < 10; ++l) s[l] = Sd[(static_cast<size_t>(l) * 3 + c) * SMPL_VP + v];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float sh = 0.f;
-#pragma unroll
-                for (int l = 0; l < 10; ++l) sh = fmaf(sm.beta[warp * 4 + i][l], s[l], sh);
-                vs[i][c] = (t + sh) + acc[i][h][c];             // v_posed = v_shaped + pose offsets
-            }
-        }
-        // skinning: T = sum_j w_j A_j  (3x4), v = T [v_posed; 1]
-        float T[4][12];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int e = 0; e < 12; ++e) T[i][e] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+        const int img = warp * 8 + i;
+        float o[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll 4
         for (int j = 0; j < 24; ++j) {
-            const float w = Wl[static_cast<size_t>(j) * SMPL_VP + v];
+            const float2 w = *reinterpret_cast<const float2*>(&sm.W[j][2 * lane]);
+            const float4* Aj = reinterpret_cast<const float4*>(&sm.A[img][j][0]);
+            const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4* Aj = reinterpret_cast<const float4*>(&sm.A[warp * 4 + i][j][0]);
-                const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-                T[i][0] = fmaf(w, r0.x, T[i][0]); T[i][1] = fmaf(w, r0.y, T[i][1]); T[i][2] = fmaf(w, r0.z, T[i][2]); T[i][3] = fmaf(w, r0.w, T[i][3]);
-                T[i][4] = fmaf(w, r1.x, T[i][4]); T[i][5] = fmaf(w, r1.y, T[i][5]); T[i][6] = fmaf(w, r1.z, T[i][6]); T[i][7] = fmaf(w, r1.w, T[i][7]);
-                T[i][8] = fmaf(w, r2.x, T[i][8]); T[i][9] = fmaf(w, r2.y, T[i][9]); T[i][10] = fmaf(w, r2.z, T[i][10]); T[i][11] = fmaf(w, r2.w, T[i][11]);
+            for (int h = 0; h < 2; ++h) {
+                const float x = acc[i][h][0], y = acc[i][h][1], z = acc[i][h][2], wh = h ? w.y : w.x;
+                o[h][0] = fmaf(wh, fmaf(r0.x, x, fmaf(r0.y, y, fmaf(r0.z, z, r0.w))), o[h][0]);
+                o[h][1] = fmaf(wh, fmaf(r1.x, x, fmaf(r1.y, y, fmaf(r1.z, z, r1.w))), o[h][1]);
+                o[h][2] = fmaf(wh, fmaf(r2.x, x, fmaf(r2.y, y, fmaf(r2.z, z, r2.w))), o[h][2]);
             }
         }
-        float jx[9];
+        const int b = b0 + img;
+        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 9; ++q) jx[q] = Jx[static_cast<size_t>(q) * SMPL_VP + v];
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float o[3];
+            for (int c = 0; c < 3; ++c) tr[(2 * lane + h) * 3 + c] = o[h][c];
+        __syncwarp();
+        if (b < B) {
+            float* dst = o_verts + b * ld_verts + static_cast<size_t>(v0) * 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                o[c] = T[i][c * 4 + 0] * vs[i][0] + T[i][c * 4 + 1] * vs[i][1] + T[i][c * 4 + 2] * vs[i][2] + T[i][c * 4 + 3];
-            const int b = b0 + warp * 4 + i;
-            if (b < B && v < SMPL_NV) {
-                float* dst = o_verts + b * ld_verts + static_cast<size_t>(v) * 3;
-                dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+            for (int q = 0; q < 6; ++q) {
+                const int f = q * 32 + lane;
+                if (v0 * 3 + f < SMPL_NV * 3) dst[f] = tr[f];
             }
-#pragma unroll
-            for (int q = 0; q < 9; ++q)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) ej[i][q * 3 + c] = fmaf(jx[q], o[c], ej[i][q * 3 + c]);
-        }
-    }
-    // extra-joint partials: reduce the tile's 64 vertices (fixed order), one record per (image, vertex tile)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int b = b0 + warp * 4 + i;
-#pragma unroll
-        for (int q = 0; q < 27; ++q) {
-            const float s = warp_sum(ej[i][q]);
-            if (lane == 0 && b < B) partials[(static_cast<size_t>(b) * SMPL_NVT + blockIdx.x) * 27 + q] = s;
         }
     }
 }
 
-bool smpl_verts_launch(const float* Vt, const float* Sd, const float* Pd, const float* Wl, const float* Jx, const float* X,
-                       int ldx, int C, const float* pf, const float* Amat, float* o_verts, long long ld_verts,
-                       float* partials, int B, cudaStream_t s) {
+bool smpl_verts_launch(const float* Vt, const float* Sd, const float* Pd, const float* Wl, const float* X, int ldx, int C,
+                       const float* pf, const float* Amat, float* o_verts, long long ld_verts, int B, cudaStream_t s) {
     static DeviceOnce attr;
     if (attr.need()) {
         if (!check_cuda(cudaFuncSetAttribute(smpl_verts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(SvSmem))), "smpl_verts attr")) return false;
     }
     dim3 grid(SMPL_NVT, (B + SV_TB - 1) / SV_TB);
-    smpl_verts_kernel<<<grid, 256, sizeof(SvSmem), s>>>(Vt, Sd, Pd, Wl, Jx, X, ldx, C, pf, Amat, o_verts, ld_verts, partials, B);
+    smpl_verts_kernel<<<grid, 256, sizeof(SvSmem), s>>>(Vt, Sd, Pd, Wl, X, ldx, C, pf, Amat, o_verts, ld_verts, B);
     return check_cuda(cudaGetLastError(), "smpl_verts");
 }
 
 // ------------------------------------------------------------------ 49 joints, camera, projection
-// grid = B, block = 64.
-__global__ void __launch_bounds__(64)
+// grid = B, block = 256.  All 256 threads first regress the 9 extra joints from the image's vertices (thread t takes the
+// vertices t, t+256, ...; fixed-order shuffle + shared-memory reduction, so the result is deterministic); the first 64 then
+// do what the kernel always did.
+__global__ void __launch_bounds__(256)
 smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const float* __restrict__ Jposed,
-                   const float* __restrict__ partials, const float* __restrict__ X, int ldx, int C,
+                   const float* __restrict__ Jx, const float* __restrict__ X, int ldx, int C,
                    const float* __restrict__ cam_rotmat, const float* __restrict__ cam_intr,
                    const float* __restrict__ bbox_scale, const float* __restrict__ bbox_center,
                    const float* __restrict__ img_w, const float* __restrict__ img_h,
@@ -424,7 +434,29 @@ smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const fl
 {
     __shared__ float j54[54][3];
     __shared__ float s_t[3];
+    __shared__ float s_ej[8][27];
     const int b = blockIdx.x, t = threadIdx.x;
+    {
+        float ej[27];
+#pragma unroll
+        for (int q = 0; q < 27; ++q) ej[q] = 0.f;
+        const float* vb = verts + b * ld_verts;
+#pragma unroll 3
+        for (int v = t; v < SMPL_NV; v += 256) {
+            const float x = vb[static_cast<size_t>(v) * 3 + 0], y = vb[static_cast<size_t>(v) * 3 + 1], z = vb[static_cast<size_t>(v) * 3 + 2];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const float w = Jx[static_cast<size_t>(q) * SMPL_VP + v];
+                ej[q * 3 + 0] = fmaf(w, x, ej[q * 3 + 0]); ej[q * 3 + 1] = fmaf(w, y, ej[q * 3 + 1]); ej[q * 3 + 2] = fmaf(w, z, ej[q * 3 + 2]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
+            const float s = warp_sum(ej[q]);
+            if ((t & 31) == 0) s_ej[t >> 5][q] = s;
+        }
+    }
+    __syncthreads();
     if (t < 24) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) j54[t][c] = Jposed[(static_cast<size_t>(b) * 24 + t) * 3 + c];
@@ -434,8 +466,8 @@ smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const fl
     } else if (t < 54) {
         const int q = t - 45;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        const float* p = partials + static_cast<size_t>(b) * SMPL_NVT * 27 + q * 3;
-        for (int vt = 0; vt < SMPL_NVT; ++vt) { s0 += p[vt * 27 + 0]; s1 += p[vt * 27 + 1]; s2 += p[vt * 27 + 2]; }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { s0 += s_ej[w][q * 3 + 0]; s1 += s_ej[w][q * 3 + 1]; s2 += s_ej[w][q * 3 + 2]; }
         j54[t][0] = s0; j54[t][1] = s1; j54[t][2] = s2;
     }
     const float* cam = X + static_cast<size_t>(b) * ldx + C + 154;
@@ -485,12 +517,12 @@ smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const fl
     }
 }
 
-bool smpl_joints_launch(const float* verts, long long ld_verts, const float* Jposed, const float* partials, const float* X,
+bool smpl_joints_launch(const float* verts, long long ld_verts, const float* Jposed, const float* Jx, const float* X,
                         int ldx, int C, const float* cam_rotmat, const float* cam_intr, const float* bbox_scale,
                         const float* bbox_center, const float* img_w, const float* img_h, float* o_j3d, long long ld_j3d,
                         float* o_j2d, long long ld_j2d, float* o_camt, long long ld_camt, int use_cam, float focal_length,
                         float img_res, int B, cudaStream_t s) {
-    smpl_joints_kernel<<<B, 64, 0, s>>>(verts, ld_verts, Jposed, partials, X, ldx, C, cam_rotmat, cam_intr, bbox_scale,
+    smpl_joints_kernel<<<B, 256, 0, s>>>(verts, ld_verts, Jposed, Jx, X, ldx, C, cam_rotmat, cam_intr, bbox_scale,
                                         bbox_center, img_w, img_h, o_j3d, ld_j3d, o_j2d, ld_j2d, o_camt, ld_camt,
                                         use_cam, focal_length, img_res, B);
     return check_cuda(cudaGetLastError(), "smpl_joints");

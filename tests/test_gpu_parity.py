@@ -250,6 +250,19 @@ def test_joint_gather_bit_exact(models):
     assert torch.allclose(torch.linalg.det(R), torch.ones(R.shape[0], device=R.device), atol=1e-5)
 
 
+def test_smpl_kernels_isolated_from_trunk(models):
+    """smpl_prep / smpl_verts / smpl_joints alone: the oracle's SMPL49 (oracle/head.py::lbs, restating smplx.lbs A.4) is fed the
+    pose / shape THE PRODUCT predicted, so backbone and head deviations drop out and the fp32 LBS kernels are held to fp32
+    round-off (1e-5 absolute; measured error is printed by the assert on failure) instead of the 1e-3 vertex tolerance of the full path.  B = 70 spans two 64-image tiles of the
+    vertex kernel, the second one ragged with idle warps."""
+    cc, _, hmr, hmr_ref = models
+    b = synthetic_batch(70, seed=11)
+    got = _run_product(cc, hmr, b, 'bf16')
+    verts, j49 = hmr_ref.smpl.smpl(got['pred_pose'].cpu().reshape(-1, 24, 3, 3), got['pred_shape'].cpu())
+    _assert_close('verts | product pose', got['smpl_vertices'], verts, atol=1e-5, rtol=1e-5)
+    _assert_close('joints3d | product pose', got['smpl_joints3d'], j49, atol=1e-5, rtol=1e-5)
+
+
 # --------------------------------------------------------------------------------------- 16-bit tensor-core modes
 @pytest.mark.parametrize('precision', ['bf16', 'fp16'])
 def test_full_forward_lowp_parity(models, precision):
