@@ -112,7 +112,9 @@ int specb200_camtail_add_linear(specb200_camtail_t* t, int32_t which, const floa
                                 int32_t out_features, int32_t in_features);
 int specb200_camtail_finalize(specb200_camtail_t* t);
 int64_t specb200_camtail_workspace_bytes(specb200_camtail_t* t, int32_t batch);
-/* logits_out_dev: fp32 [batch][3*num_out] = [vfov | pitch | roll] logits. */
+/* logits_out_dev: fp32 [batch][3*num_out] = [vfov | pitch | roll] logits.  workspace_dev (>= specb200_camtail_workspace_bytes)
+ * is always required: hidden activations of multi-layer heads, or the split-K partial sums of the fused single-layer GEMM.
+ * Calls on ONE handle must be stream-ordered with each other (the split-K arrival counters belong to the handle). */
 int specb200_camtail_forward(specb200_camtail_t* t, const float* pooled_dev, int32_t pooled_ld, int32_t batch,
                              void* workspace_dev, int64_t workspace_bytes, float* logits_out_dev, void* stream);
 /* logits -> angles_out_dev [batch][3] (vfov,pitch,roll radians).  If rotmat_out_dev != NULL also writes

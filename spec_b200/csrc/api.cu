@@ -29,6 +29,11 @@ bool check_cuda(cudaError_t e, const char* what) {
     return false;
 }
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SPECB200_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int prec_elem(int prec) { return prec == PREC_F32 ? 4 : 2; }
 
@@ -547,7 +552,9 @@ struct specb200_camtail {
     bool fused = false;                 // single-layer heads concatenated into one [3*num_out][in] GEMM
     float* wcat = nullptr; float* bcat = nullptr;
     int max_hidden = 0;
+    unsigned* red_counters = nullptr;   // split-K arrival counters of the fused GEMM (library-owned: they must start at zero)
 };
+constexpr int CAM_RED_COUNTERS = 4096, CAM_RED_SLICES = 8;
 
 extern "C" int specb200_camtail_create(specb200_camtail_t** out, int32_t in_features, int32_t num_out) {
     if (!out || in_features <= 0 || num_out <= 0) { set_error("camtail_create: bad arguments"); return 1; }
@@ -585,6 +592,8 @@ extern "C" int specb200_camtail_finalize(specb200_camtail_t* t) {
             if (!check_cuda(cudaMemcpy(t->wcat + h * wsz, t->heads[h][0].w, sizeof(float) * wsz, cudaMemcpyDeviceToDevice), "copy")) return 1;
             if (!check_cuda(cudaMemcpy(t->bcat + h * t->num_out, t->heads[h][0].b, sizeof(float) * t->num_out, cudaMemcpyDeviceToDevice), "copy")) return 1;
         }
+        if (!check_cuda(cudaMalloc(&t->red_counters, sizeof(unsigned) * CAM_RED_COUNTERS), "cudaMalloc") ||
+            !check_cuda(cudaMemset(t->red_counters, 0, sizeof(unsigned) * CAM_RED_COUNTERS), "cudaMemset")) return 1;
         t->fused = true;
     }
     return 0;
@@ -592,6 +601,8 @@ extern "C" int specb200_camtail_finalize(specb200_camtail_t* t) {
 
 extern "C" int64_t specb200_camtail_workspace_bytes(specb200_camtail_t* t, int32_t batch) {
     if (!t || batch <= 0) { set_error("camtail_workspace_bytes: bad arguments"); return -1; }
+    if (t->fused)        // split-K partial sums of the one concatenated GEMM
+        return static_cast<int64_t>(align_up(static_cast<size_t>(CAM_RED_SLICES) * batch * 3 * t->num_out * sizeof(float), 256) + 256);
     return static_cast<int64_t>(2 * align_up(static_cast<size_t>(batch) * std::max(t->max_hidden, 4) * sizeof(float), 256) + 256);
 }
 
@@ -601,9 +612,15 @@ extern "C" int specb200_camtail_forward(specb200_camtail_t* t, const float* pool
     NvtxRange nvtx_cam("specb200:camcalib_fc");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int ldo = 3 * t->num_out;
-    if (t->fused)
-        return linear_f32_launch(pooled, pooled_ld, t->wcat, t->in_features, t->bcat, nullptr, 0, logits_out, ldo, batch, ldo, t->in_features, s) ? 0 : 1;
     if (!workspace || workspace_bytes < specb200_camtail_workspace_bytes(t, batch)) { set_error("camtail_forward: workspace too small"); return 1; }
+    if (t->fused) {
+        LinearRedWs red;
+        red.partial = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+        red.partial_floats = static_cast<size_t>(CAM_RED_SLICES) * batch * ldo;
+        red.counters = t->red_counters; red.n_counters = CAM_RED_COUNTERS;
+        return linear_f32_launch(pooled, pooled_ld, t->wcat, t->in_features, t->bcat, nullptr, 0, logits_out, ldo, batch, ldo, t->in_features, s,
+                                 1, 0, nullptr, &red) ? 0 : 1;
+    }
     float* tmp[2];
     tmp[0] = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
     tmp[1] = tmp[0] + align_up(static_cast<size_t>(batch) * t->max_hidden, 64);
@@ -636,6 +653,7 @@ extern "C" void specb200_camtail_destroy(specb200_camtail_t* t) {
     for (int h = 0; h < 3; ++h) for (auto& l : t->heads[h]) { cudaFree(l.w); cudaFree(l.b); }
     if (t->wcat) cudaFree(t->wcat);
     if (t->bcat) cudaFree(t->bcat);
+    if (t->red_counters) cudaFree(t->red_counters);
     delete t;
 }
 

@@ -54,6 +54,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization (internal.h::launch_dep) may start as soon as every
+// CTA of its stream predecessor has executed griddep_launch() or exited; its CTAs then run their set-up (barrier init, TMEM
+// allocation, descriptor prefetch, bias staging -- nothing that reads activations or writes global memory) on SMs the
+// predecessor has already left, and block in griddep_wait() until the predecessor grid has COMPLETED and its writes are visible.
+// Rule kept by every kernel that is launched this way: griddep_wait() is executed by all threads that go on to touch global
+// activations, before the first such access and before any early return.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- cp.async (LDGSTS)
 // 16-byte copy, zero-filled when !valid (src-size 0).  src must still be a legal address.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {

@@ -97,6 +97,7 @@ template <typename T, int CIN, bool TRACE = false>
 __global__ void __launch_bounds__(BK_THREADS, 1)
 bottleneck64_kernel(const BneckParams p, const __grid_constant__ BneckMaps maps, const __grid_constant__ BneckBias bias)
 {
+    griddep_launch();
     auto stamp = [&](uint32_t tc, int slot) {
         if constexpr (TRACE) {
             if (blockIdx.x == 0 && tc < BK_TRACE_TILES) p.trace[tc * BK_TRACE_SLOTS + slot] = clock64();
@@ -134,6 +135,7 @@ bottleneck64_kernel(const BneckParams p, const __grid_constant__ BneckMaps maps,
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();
     const uint32_t tmem_base = *tmem_ptr_s;
     const uint32_t acc1 = tmem_base, acc2 = tmem_base + 128, acc3 = tmem_base + 256;
 
@@ -428,7 +430,7 @@ bool bneck_trace_run(BneckParams p, const BneckMaps& maps, const BneckBias& bias
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = static_cast<unsigned>(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-    kern<<<grid, BK_THREADS, L::DYN_BYTES, s>>>(p, maps, bias);
+    launch_dep(kern, dim3(grid), dim3(BK_THREADS), L::DYN_BYTES, s, p, maps, bias);
     bool ok = check_cuda(cudaStreamSynchronize(s), "bottleneck trace run");
     std::vector<long long> h(n);
     ok = ok && check_cuda(cudaMemcpy(h.data(), p.trace, n * 8, cudaMemcpyDeviceToHost), "trace copy");
@@ -485,7 +487,7 @@ bool bneck_launch_t(const BottleneckArgs& a, cudaStream_t s) {
         if (!check_cuda(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev), "sm count")) return false;
     }
     const unsigned grid = static_cast<unsigned>(total < num_sms ? total : num_sms);
-    kern<<<grid, BK_THREADS, L::DYN_BYTES, s>>>(p, maps, bias);
+    launch_dep(kern, dim3(grid), dim3(BK_THREADS), L::DYN_BYTES, s, p, maps, bias);
     return check_cuda(cudaGetLastError(), "bottleneck launch");
 }
 }  // namespace

@@ -63,6 +63,7 @@ template <typename T, int BLOCK_N, int PA, int PB, bool B_RESIDENT, int G>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv3x3_halo_kernel(const ConvParams p, const __grid_constant__ HaloMaps maps, int tiles_w, int tiles_h, int total_tiles)
 {
+    griddep_launch();
     using L = HaloSmem<BLOCK_N, PA, PB, G>;
     using D = HaloDims<G>;
     constexpr int HL_TH = D::TH, HL_TW = D::TW, HL_PW = D::PW, HL_PATCH_TX = D::PATCH_TX, HL_PATCH_BYTES = D::PATCH_BYTES;
@@ -100,6 +101,7 @@ conv3x3_halo_kernel(const ConvParams p, const __grid_constant__ HaloMaps maps, i
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();
     const uint32_t tmem_base = *tmem_ptr_s;
 
     auto decode = [&](int tile, int& n, int& oh0, int& ow0) {
@@ -353,7 +355,7 @@ static bool halo_launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStrea
     const long long total = static_cast<long long>(p.N) * tiles_w * tiles_h;
     if (total > 0x7fffffffLL) { set_error("conv_halo: too many tiles"); return false; }
     const unsigned grid = static_cast<unsigned>(total < num_sms ? total : num_sms);
-    kern<<<grid, HL_THREADS, L::DYN_BYTES, s>>>(p, maps, tiles_w, tiles_h, static_cast<int>(total));
+    launch_dep(kern, dim3(grid), dim3(HL_THREADS), L::DYN_BYTES, s, p, maps, tiles_w, tiles_h, static_cast<int>(total));
     return check_cuda(cudaGetLastError(), "conv_halo launch");
 }
 

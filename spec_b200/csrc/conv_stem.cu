@@ -228,6 +228,7 @@ conv_stem7p_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __
                    const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
                    int tiles_h, int tiles_w, int total_tiles)
 {
+    griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -262,6 +263,7 @@ conv_stem7p_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();
     const uint32_t tmem_base = *tmem_ptr_s;
 
     if (warp >= 4 && warp < STP_MMA_WARP) {
@@ -481,9 +483,9 @@ bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N,
         }
         const unsigned gridp = static_cast<unsigned>(total < num_sms ? total : num_sms);
         if (prec == PREC_BF16)
-            conv_stem7p_kernel<__nv_bfloat16><<<gridp, STP_THREADS, STP_DYN_BYTES, s>>>(tmap_img, w.bias, w.tmap_b, tmap_out, tiles_h, tiles_w, static_cast<int>(total));
+            launch_dep(conv_stem7p_kernel<__nv_bfloat16>, dim3(gridp), dim3(STP_THREADS), STP_DYN_BYTES, s, tmap_img, w.bias, w.tmap_b, tmap_out, tiles_h, tiles_w, static_cast<int>(total));
         else if (prec == PREC_F16)
-            conv_stem7p_kernel<__half><<<gridp, STP_THREADS, STP_DYN_BYTES, s>>>(tmap_img, w.bias, w.tmap_b, tmap_out, tiles_h, tiles_w, static_cast<int>(total));
+            launch_dep(conv_stem7p_kernel<__half>, dim3(gridp), dim3(STP_THREADS), STP_DYN_BYTES, s, tmap_img, w.bias, w.tmap_b, tmap_out, tiles_h, tiles_w, static_cast<int>(total));
         else { set_error("conv_stem7: 16-bit precisions only"); return false; }
         return check_cuda(cudaGetLastError(), "conv_stem7p launch");
     }

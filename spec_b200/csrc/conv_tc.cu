@@ -76,6 +76,7 @@ template <typename T, int BLOCK_N, int STAGES, int A_MODE>
 __global__ void __launch_bounds__(CONV_TC_THREADS)
 conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int n_tiles)
 {
+    griddep_launch();
     static_assert(GATHER_LAG <= STAGES - 1, "producer lag must leave one free stage");
     using L = ConvTcSmem<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
@@ -128,6 +129,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();
     const uint32_t tmem_acc = *tmem_ptr_s;
 
     if (warp < 4 || warp >= 6) {
@@ -437,6 +439,7 @@ template <typename T, int BLOCK_N, int STAGES, int A_MODE>
 __global__ void __launch_bounds__(CONV_TCP_THREADS, 1)
 conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int n_tiles, int total_tiles)
 {
+    griddep_launch();
     static_assert(A_MODE == A_TILED || A_MODE == A_IM2COL, "persistent kernel is TMA-fed");
     using L = ConvTcpSmem<BLOCK_N, STAGES>;
     constexpr int NBUF = L::EPI_BUFS;
@@ -483,6 +486,7 @@ conv_tcp_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_wait();
     const uint32_t tmem_base = *tmem_ptr_s;
 
     if (warp == 0) {
@@ -785,8 +789,8 @@ static bool launch_pair(const ConvParams& p, ConvTcMaps maps, const ConvWeights&
     if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles"); return false; }
     const long long pairs = g_num_sms / 2;
     const unsigned grid = 2u * static_cast<unsigned>(total < pairs ? total : pairs);
-    if (mode == A_TILED) k0<<<grid, CONV_TCP_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles, static_cast<int>(total));
-    else k1<<<grid, CONV_TCP_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles, static_cast<int>(total));
+    if (mode == A_TILED) launch_dep(k0, dim3(grid), dim3(CONV_TCP_THREADS), L::DYN_BYTES, s, p, maps, n_tiles, static_cast<int>(total));
+    else launch_dep(k1, dim3(grid), dim3(CONV_TCP_THREADS), L::DYN_BYTES, s, p, maps, n_tiles, static_cast<int>(total));
     return check_cuda(cudaGetLastError(), "conv_tcp2 launch");
 }
 
@@ -808,8 +812,8 @@ static bool launch_persistent(const ConvParams& p, const ConvTcMaps& maps, int m
     const long long total = static_cast<long long>(m_tiles) * n_tiles;
     if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles"); return false; }
     const unsigned grid = static_cast<unsigned>(total < g_num_sms ? total : g_num_sms);
-    if (mode == A_TILED) k0<<<grid, CONV_TCP_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles, static_cast<int>(total));
-    else k1<<<grid, CONV_TCP_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles, static_cast<int>(total));
+    if (mode == A_TILED) launch_dep(k0, dim3(grid), dim3(CONV_TCP_THREADS), L::DYN_BYTES, s, p, maps, n_tiles, static_cast<int>(total));
+    else launch_dep(k1, dim3(grid), dim3(CONV_TCP_THREADS), L::DYN_BYTES, s, p, maps, n_tiles, static_cast<int>(total));
     return check_cuda(cudaGetLastError(), "conv_tcp launch");
 }
 
@@ -870,10 +874,10 @@ static bool launch_cfg(const ConvParams& p, const ConvWeights& w, cudaStream_t s
     const long long grid = static_cast<long long>(m_tiles) * n_tiles;
     if (grid > 0x7fffffffLL) { set_error("conv_tc: grid too large"); return false; }
     const unsigned g = static_cast<unsigned>(grid);
-    if (mode == A_TILED) k0<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
-    else if (mode == A_IM2COL) k1<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
-    else if (mode == A_STEM) k3<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
-    else k2<<<g, CONV_TC_THREADS, L::DYN_BYTES, s>>>(p, maps, n_tiles);
+    if (mode == A_TILED) launch_dep(k0, g, dim3(CONV_TC_THREADS), L::DYN_BYTES, s, p, maps, n_tiles);
+    else if (mode == A_IM2COL) launch_dep(k1, g, dim3(CONV_TC_THREADS), L::DYN_BYTES, s, p, maps, n_tiles);
+    else if (mode == A_STEM) launch_dep(k3, g, dim3(CONV_TC_THREADS), L::DYN_BYTES, s, p, maps, n_tiles);
+    else launch_dep(k2, g, dim3(CONV_TC_THREADS), L::DYN_BYTES, s, p, maps, n_tiles);
     return check_cuda(cudaGetLastError(), "conv_tc launch");
 }
 

@@ -33,6 +33,7 @@ template <typename T, int BLOCK_N, int STAGES, int A_MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_TCP_THREADS, 1)
 conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, int n_tiles, int total_tiles /* pair tiles */)
 {
+    griddep_launch();
     static_assert(A_MODE == A_TILED || A_MODE == A_IM2COL, "pair kernel is TMA-fed");
     using L = ConvTc2Smem<BLOCK_N, STAGES>;
     constexpr int NBUF = L::EPI_BUFS;
@@ -79,6 +80,7 @@ conv_tcp2_kernel(const ConvParams p, const __grid_constant__ ConvTcMaps maps, in
     tc_fence_before();
     cluster_sync_all();                                            // both CTAs' barriers and TMEM are ready
     tc_fence_after();
+    griddep_wait();
     const uint32_t tmem_base = *tmem_ptr_s;
 
     if (warp == 0) {

@@ -43,6 +43,8 @@ static inline unsigned nblk(long long n, int t) { return static_cast<unsigned>((
 // ------------------------------------------------------------------ images NCHW f32 -> NHWC(cpad)
 template <typename T>
 __global__ void images_to_nhwc_kernel(const float* __restrict__ img, T* __restrict__ out, long long npix, int HW) {
+    griddep_launch();
+    griddep_wait();
     // NHWC with 4 channels (RGB + one zero): 16 B / pixel in fp32, 8 B / pixel in the 16-bit modes
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= npix) return;
@@ -62,7 +64,7 @@ __global__ void images_to_nhwc_kernel(const float* __restrict__ img, T* __restri
 bool images_to_nhwc_launch(const float* img, void* out, int N, int H, int W, int cpad, int prec, cudaStream_t s) {
     const long long npix = static_cast<long long>(N) * H * W;
     if (cpad != 4) { set_error("images_to_nhwc: the image buffer must have 4 channels"); return false; }
-    SB_DISPATCH_PREC(prec, (images_to_nhwc_kernel<T><<<nblk(npix, 256), 256, 0, s>>>(img, static_cast<T*>(out), npix, H * W)));
+    SB_DISPATCH_PREC(prec, (launch_dep(images_to_nhwc_kernel<T>, dim3(nblk(npix, 256)), dim3(256), 0, s, img, static_cast<T*>(out), npix, H * W)));
     return check_cuda(cudaGetLastError(), "images_to_nhwc");
 }
 
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256, 1)
 maxpool_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out, int tiles_w, int tiles_h,
                    int total_tiles)
 {
+    griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t patch_s = sbase, st_s = sbase + 2 * MP_PATCH_BYTES, bar_full = st_s + 2 * MP_ST_BYTES;
@@ -131,6 +134,7 @@ maxpool_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         tma_prefetch_desc(&tmap_in); tma_prefetch_desc(&tmap_out);
     }
     __syncthreads();
+    griddep_wait();
     auto issue = [&](int tile, uint32_t b) {
         const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
         mbar_arrive_expect_tx(bar_full + b * 8, MP_PATCH_TX);
@@ -208,8 +212,8 @@ bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, 
         const long long total = static_cast<long long>(N) * tiles_w * tiles_h;
         if (total > 0x7fffffffLL) { set_error("maxpool: too many tiles"); return false; }
         const unsigned grid = static_cast<unsigned>(total < num_sms ? total : num_sms);
-        if (prec == PREC_BF16) maxpool_tma_kernel<__nv_bfloat16><<<grid, 256, MP_DYN_BYTES, s>>>(tin, tout, tiles_w, tiles_h, static_cast<int>(total));
-        else maxpool_tma_kernel<__half><<<grid, 256, MP_DYN_BYTES, s>>>(tin, tout, tiles_w, tiles_h, static_cast<int>(total));
+        if (prec == PREC_BF16) launch_dep(maxpool_tma_kernel<__nv_bfloat16>, dim3(grid), dim3(256), MP_DYN_BYTES, s, tin, tout, tiles_w, tiles_h, static_cast<int>(total));
+        else launch_dep(maxpool_tma_kernel<__half>, dim3(grid), dim3(256), MP_DYN_BYTES, s, tin, tout, tiles_w, tiles_h, static_cast<int>(total));
         return check_cuda(cudaGetLastError(), "maxpool (tma)");
     }
     SB_DISPATCH_PREC(prec, {
@@ -222,6 +226,8 @@ bool maxpool3x3s2_launch(const void* in, void* out, int N, int H, int W, int C, 
 // ------------------------------------------------------------------ acc += nearest_upsample(lo, 2^shift) [; relu]
 template <typename T>
 __global__ void upsample_add_kernel(const T* __restrict__ lo, T* __restrict__ acc, int N, int Ho, int Wo, int C, int shift, int relu) {
+    griddep_launch();
+    griddep_wait();
     constexpr int V = V16<T>::N;
     const int cv = C / V;
     const long long total = static_cast<long long>(N) * Ho * Wo * cv;
@@ -244,7 +250,7 @@ __global__ void upsample_add_kernel(const T* __restrict__ lo, T* __restrict__ ac
 bool upsample_add_launch(const void* lo, void* acc, int N, int Ho, int Wo, int C, int shift, int relu, int prec, cudaStream_t s) {
     SB_DISPATCH_PREC(prec, {
         const long long total = static_cast<long long>(N) * Ho * Wo * (C / V16<T>::N);
-        upsample_add_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(lo), static_cast<T*>(acc), N, Ho, Wo, C, shift, relu);
+        launch_dep(upsample_add_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, s, static_cast<const T*>(lo), static_cast<T*>(acc), N, Ho, Wo, C, shift, relu);
     });
     return check_cuda(cudaGetLastError(), "upsample_add");
 }
@@ -253,6 +259,8 @@ bool upsample_add_launch(const void* lo, void* acc, int N, int Ho, int Wo, int C
 template <typename T>
 __global__ void bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int Ho, int Wo,
                                 int out_ld, int out_coff) {
+    griddep_launch();
+    griddep_wait();
     constexpr int V = V16<T>::N;
     const int cv = C / V;
     const long long total = static_cast<long long>(N) * Ho * Wo * cv;
@@ -284,7 +292,7 @@ bool bilinear_launch(const void* in, void* out, int N, int H, int W, int C, int 
                      int prec, cudaStream_t s) {
     SB_DISPATCH_PREC(prec, {
         const long long total = static_cast<long long>(N) * Ho * Wo * (C / V16<T>::N);
-        bilinear_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, Ho, Wo, out_ld, out_coff);
+        launch_dep(bilinear_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, s, static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, Ho, Wo, out_ld, out_coff);
     });
     return check_cuda(cudaGetLastError(), "bilinear");
 }
@@ -292,6 +300,8 @@ bool bilinear_launch(const void* in, void* out, int N, int H, int W, int C, int 
 // ------------------------------------------------------------------ copy [rows, C] into a channel slice
 template <typename T>
 __global__ void copy_channels_kernel(const T* __restrict__ in, T* __restrict__ out, long long rows, int C, int out_ld, int out_coff) {
+    griddep_launch();
+    griddep_wait();
     constexpr int V = V16<T>::N;
     const int cv = C / V;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -303,7 +313,7 @@ __global__ void copy_channels_kernel(const T* __restrict__ in, T* __restrict__ o
 bool copy_channels_launch(const void* in, void* out, int rows, int C, int out_ld, int out_coff, int prec, cudaStream_t s) {
     SB_DISPATCH_PREC(prec, {
         const long long total = static_cast<long long>(rows) * (C / V16<T>::N);
-        copy_channels_kernel<T><<<nblk(total, 256), 256, 0, s>>>(static_cast<const T*>(in), static_cast<T*>(out), rows, C, out_ld, out_coff);
+        launch_dep(copy_channels_kernel<T>, dim3(nblk(total, 256)), dim3(256), 0, s, static_cast<const T*>(in), static_cast<T*>(out), rows, C, out_ld, out_coff);
     });
     return check_cuda(cudaGetLastError(), "copy_channels");
 }
@@ -311,6 +321,8 @@ bool copy_channels_launch(const void* in, void* out, int rows, int C, int out_ld
 // ------------------------------------------------------------------ global average pool -> fp32 [N][out_ld]
 template <typename T>
 __global__ void avgpool_kernel(const T* __restrict__ in, float* __restrict__ out, int out_ld, int N, int HW, int C) {
+    griddep_launch();
+    griddep_wait();
     constexpr int V = V16<T>::N;
     const int cv = C / V;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -334,7 +346,7 @@ __global__ void avgpool_kernel(const T* __restrict__ in, float* __restrict__ out
 bool avgpool_launch(const void* in, float* out, int out_ld, int N, int HW, int C, int prec, cudaStream_t s) {
     SB_DISPATCH_PREC(prec, {
         const long long total = static_cast<long long>(N) * (C / V16<T>::N);
-        avgpool_kernel<T><<<nblk(total, 128), 128, 0, s>>>(static_cast<const T*>(in), out, out_ld, N, HW, C);
+        launch_dep(avgpool_kernel<T>, dim3(nblk(total, 128)), dim3(128), 0, s, static_cast<const T*>(in), out, out_ld, N, HW, C);
     });
     return check_cuda(cudaGetLastError(), "avgpool");
 }

@@ -64,6 +64,20 @@ struct DeviceOnce {
 };
 bool check_cuda(cudaError_t e, const char* what);
 
+// Launch with programmatic dependent launch allowed (common.cuh: griddep_launch / griddep_wait).  ONLY for kernels that execute
+// griddep_wait() before they touch global activations; SPECB200_PDL=0 turns the attribute off (plain stream order).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);     // errors surface through cudaGetLastError at the call site
+}
+
 // tcgen05 implicit-GEMM conv (conv_tc.cu).  prec is PREC_BF16 or PREC_F16.
 bool conv_tc_launch(const ConvParams& p, const ConvWeights& w, int prec, cudaStream_t s);
 bool conv_tc_make_weight_tmap(ConvWeights& w);
@@ -99,10 +113,14 @@ bool conv_stem7_launch(const float* img, void* out, const ConvWeights& w, int N,
 bool conv_f32_launch(const ConvParams& p, const ConvWeights& w, cudaStream_t s);
 // out[M, n0:n0+N] (ld out_ld) = A[M,K](ld lda) @ W[N,K]^T (ld ldw) + bias[N] + add[M,N](ld add_ld) ; fp32
 // ksplit > 1: split-K partial sums, slice z written to out + z*split_stride (consumer adds them in order); the number of slices
-// actually written is returned in *ksplit_used (<= ksplit) -- the consumer must sum exactly that many
+// actually written is returned in *ksplit_used (<= ksplit) -- the consumer must sum exactly that many.
+// red != nullptr (and split_stride == 0): the launch picks its own split-K factor and reduces inside the kernel, in a fixed
+// order, through this scratch: `partial` needs no initialisation, `counters` must be zero before the first launch (the kernel
+// leaves them zero) and must not be shared by launches that can run concurrently.
+struct LinearRedWs { float* partial; size_t partial_floats; unsigned* counters; int n_counters; };
 bool linear_f32_launch(const float* A, int lda, const float* W, int ldw, const float* bias, const float* add,
                        int add_ld, float* out, int out_ld, int M, int N, int K, cudaStream_t s, int ksplit = 1,
-                       size_t split_stride = 0, int* ksplit_used = nullptr);
+                       size_t split_stride = 0, int* ksplit_used = nullptr, const LinearRedWs* red = nullptr);
 
 // eval-side metrics (eval.cu)
 bool eval_launch(const float* JT, const int* map14, int B, const float* pred_verts, long long ld_pred, const float* gt_kp14,
