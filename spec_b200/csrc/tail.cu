@@ -420,12 +420,60 @@ bool smpl_verts_launch(const float* Vt, const float* Sd, const float* Pd, const 
 }
 
 // ------------------------------------------------------------------ 49 joints, camera, projection
-// grid = B, block = 256.  All 256 threads first regress the 9 extra joints from the image's vertices (thread t takes the
-// vertices t, t+256, ...; fixed-order shuffle + shared-memory reduction, so the result is deterministic); the first 64 then
-// do what the kernel always did.
+// The 9 extra joints (J_regressor_extra @ vertices): CTA (x, y) handles the images 8x .. 8x+7 (one per warp) and the y-th
+// quarter of the vertices (7 chunks of 256), so the regressor is read once per 8 images (one image per CTA re-read all 248 KB
+// of it from L2 per image: 34 us at B = 256) and 4 * B/8 CTAs share the work.  Per chunk a lane first issues all 24 loads of
+// its 8 vertices, then the chunk of the regressor is staged through shared memory, then 8 x 27 FMAs.  One fixed-order shuffle
+// tree per output; the four quarter sums are added in order by smpl_joints_kernel -- deterministic.
+constexpr int EJ_SPLIT = 4, EJ_CHUNKS = (SMPL_VP / 256 + EJ_SPLIT - 1) / EJ_SPLIT;
 __global__ void __launch_bounds__(256)
+smpl_extra_joints_kernel(const float* __restrict__ verts, long long ld_verts, const float* __restrict__ Jx,
+                         float* __restrict__ ej_out /*[B][EJ_SPLIT][27]*/, int B)
+{
+    __shared__ float sJ[9][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    const float* vb = verts + (b < B ? b : 0) * ld_verts;
+    float ej[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) ej[q] = 0.f;
+    const int c_begin = blockIdx.y * EJ_CHUNKS * 256;
+    const int c_end = min(SMPL_NV, c_begin + EJ_CHUNKS * 256);
+    for (int c0 = c_begin; c0 < c_end; c0 += 256) {
+        float vx[8][3];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int v = c0 + k * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) vx[k][c] = (v < SMPL_NV) ? vb[static_cast<size_t>(v) * 3 + c] : 0.f;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 9 * 256; i += 256) {
+            const int q = i >> 8, v = i & 255;
+            sJ[q][v] = (c0 + v < SMPL_NV) ? Jx[static_cast<size_t>(q) * SMPL_VP + c0 + v] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const float w = sJ[q][k * 32 + lane];
+                ej[q * 3 + 0] = fmaf(w, vx[k][0], ej[q * 3 + 0]); ej[q * 3 + 1] = fmaf(w, vx[k][1], ej[q * 3 + 1]);
+                ej[q * 3 + 2] = fmaf(w, vx[k][2], ej[q * 3 + 2]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 27; ++q) {
+        const float s = warp_sum(ej[q]);
+        if (lane == 0 && b < B) ej_out[(static_cast<size_t>(b) * EJ_SPLIT + blockIdx.y) * 27 + q] = s;
+    }
+}
+
+// grid = B, block = 64.
+__global__ void __launch_bounds__(64)
 smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const float* __restrict__ Jposed,
-                   const float* __restrict__ Jx, const float* __restrict__ X, int ldx, int C,
+                   const float* __restrict__ ej, const float* __restrict__ X, int ldx, int C,
                    const float* __restrict__ cam_rotmat, const float* __restrict__ cam_intr,
                    const float* __restrict__ bbox_scale, const float* __restrict__ bbox_center,
                    const float* __restrict__ img_w, const float* __restrict__ img_h,
@@ -434,29 +482,7 @@ smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const fl
 {
     __shared__ float j54[54][3];
     __shared__ float s_t[3];
-    __shared__ float s_ej[8][27];
     const int b = blockIdx.x, t = threadIdx.x;
-    {
-        float ej[27];
-#pragma unroll
-        for (int q = 0; q < 27; ++q) ej[q] = 0.f;
-        const float* vb = verts + b * ld_verts;
-#pragma unroll 3
-        for (int v = t; v < SMPL_NV; v += 256) {
-            const float x = vb[static_cast<size_t>(v) * 3 + 0], y = vb[static_cast<size_t>(v) * 3 + 1], z = vb[static_cast<size_t>(v) * 3 + 2];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) {
-                const float w = Jx[static_cast<size_t>(q) * SMPL_VP + v];
-                ej[q * 3 + 0] = fmaf(w, x, ej[q * 3 + 0]); ej[q * 3 + 1] = fmaf(w, y, ej[q * 3 + 1]); ej[q * 3 + 2] = fmaf(w, z, ej[q * 3 + 2]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 27; ++q) {
-            const float s = warp_sum(ej[q]);
-            if ((t & 31) == 0) s_ej[t >> 5][q] = s;
-        }
-    }
-    __syncthreads();
     if (t < 24) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) j54[t][c] = Jposed[(static_cast<size_t>(b) * 24 + t) * 3 + c];
@@ -465,9 +491,10 @@ smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const fl
         j54[t][0] = v[0]; j54[t][1] = v[1]; j54[t][2] = v[2];
     } else if (t < 54) {
         const int q = t - 45;
+        const float* e = ej + static_cast<size_t>(b) * EJ_SPLIT * 27 + q * 3;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { s0 += s_ej[w][q * 3 + 0]; s1 += s_ej[w][q * 3 + 1]; s2 += s_ej[w][q * 3 + 2]; }
+        for (int y = 0; y < EJ_SPLIT; ++y) { s0 += e[y * 27 + 0]; s1 += e[y * 27 + 1]; s2 += e[y * 27 + 2]; }
         j54[t][0] = s0; j54[t][1] = s1; j54[t][2] = s2;
     }
     const float* cam = X + static_cast<size_t>(b) * ldx + C + 154;
@@ -517,12 +544,13 @@ smpl_joints_kernel(const float* __restrict__ verts, long long ld_verts, const fl
     }
 }
 
-bool smpl_joints_launch(const float* verts, long long ld_verts, const float* Jposed, const float* Jx, const float* X,
+bool smpl_joints_launch(const float* verts, long long ld_verts, const float* Jposed, const float* Jx, float* ej_ws, const float* X,
                         int ldx, int C, const float* cam_rotmat, const float* cam_intr, const float* bbox_scale,
                         const float* bbox_center, const float* img_w, const float* img_h, float* o_j3d, long long ld_j3d,
                         float* o_j2d, long long ld_j2d, float* o_camt, long long ld_camt, int use_cam, float focal_length,
                         float img_res, int B, cudaStream_t s) {
-    smpl_joints_kernel<<<B, 256, 0, s>>>(verts, ld_verts, Jposed, Jx, X, ldx, C, cam_rotmat, cam_intr, bbox_scale,
+    smpl_extra_joints_kernel<<<dim3((B + 7) / 8, EJ_SPLIT), 256, 0, s>>>(verts, ld_verts, Jx, ej_ws, B);
+    smpl_joints_kernel<<<B, 64, 0, s>>>(verts, ld_verts, Jposed, ej_ws, X, ldx, C, cam_rotmat, cam_intr, bbox_scale,
                                         bbox_center, img_w, img_h, o_j3d, ld_j3d, o_j2d, ld_j2d, o_camt, ld_camt,
                                         use_cam, focal_length, img_res, B);
     return check_cuda(cudaGetLastError(), "smpl_joints");

@@ -21,7 +21,7 @@ bool smpl_prep_launch(const float* X, int ldx, int C, const float* Jt, const flo
                       float* o_shape, long long ld_shape, float* o_cam, long long ld_cam, int B, cudaStream_t s);
 bool smpl_verts_launch(const float* Vt, const float* Sd, const float* Pd, const float* Wl, const float* X, int ldx, int C,
                        const float* pf, const float* Amat, float* o_verts, long long ld_verts, int B, cudaStream_t s);
-bool smpl_joints_launch(const float* verts, long long ld_verts, const float* Jposed, const float* Jx, const float* X,
+bool smpl_joints_launch(const float* verts, long long ld_verts, const float* Jposed, const float* Jx, float* ej_ws /*[B][4][27]*/, const float* X,
                         int ldx, int C, const float* cam_rotmat, const float* cam_intr, const float* bbox_scale,
                         const float* bbox_center, const float* img_w, const float* img_h, float* o_j3d, long long ld_j3d,
                         float* o_j2d, long long ld_j2d, float* o_camt, long long ld_camt, int use_cam, float focal_length,
