@@ -8,6 +8,9 @@ Round-2 status (B200): the two round-1 experiments both passed the parity subset
   * SPECB200_MCAST_B        -- one-tile kernel in 2-CTA clusters sharing the weight tile by TMA multicast: parity-clean but slower
                                on the clock (layer2 3x3 0.081-0.093 vs 0.072-0.084 ms): REMOVED from the binary (profiles/README.md).
 
+  * SPECB200_PDL=0          -- trunk kernels launched in plain stream order instead of with programmatic dependent launch
+                               (the default since the end of round 2): the A/B baseline, exercised here.
+
     SPECB200_RUN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q"""
 import os
 import subprocess
@@ -20,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get('SPECB200_RUN_EXPERIMENTAL') != '1', reason='set SPECB200_RUN_EXPERIMENTAL=1 to run the non-default kernel variants')
-@pytest.mark.parametrize('switch,value', [('SPECB200_SPLIT_PRODUCER', '0'), ('SPECB200_NO_BNECK', '1')])
+@pytest.mark.parametrize('switch,value', [('SPECB200_SPLIT_PRODUCER', '0'), ('SPECB200_NO_BNECK', '1'), ('SPECB200_PDL', '0')])
 def test_non_default_variant_keeps_parity(switch, value):
     env = dict(os.environ)
     env[switch] = value
