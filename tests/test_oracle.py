@@ -77,6 +77,64 @@ def test_identity_pose_lbs_returns_shaped_template():
     assert torch.allclose(J, torch.einsum('bik,ji->bjk', v_shaped, d['J_regressor']), atol=2e-6)
 
 
+def _random_rotmats(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return og.rot6d_to_rotmat(torch.randn(n, 6, generator=g)).reshape(n, 3, 3)
+
+
+def test_lbs_root_rotation_is_rigid_about_the_root_joint():
+    """Size-independent LBS property (smplx.lbs, A.4): the pose blendshapes only see joints 1..23, so pre-multiplying the
+    ROOT rotation by Q moves every vertex and joint rigidly about the rest root joint: v' = Q (v - J0) + J0."""
+    d = {k: torch.as_tensor(v) for k, v in synthetic_smpl_data(0).items()}
+    B = 3
+    betas = torch.randn(B, 10, generator=torch.Generator().manual_seed(1))
+    R = _random_rotmats(B * 24, 2).reshape(B, 24, 3, 3)
+    Q = _random_rotmats(B, 3)
+    args = (d['v_template'], d['shapedirs'], d['posedirs'], d['J_regressor'], d['parents'].tolist(), d['lbs_weights'])
+    v, J = lbs(betas, R, *args)
+    R2 = R.clone()
+    R2[:, 0] = Q @ R[:, 0]
+    v2, J2 = lbs(betas, R2, *args)
+    v_shaped = d['v_template'][None] + torch.einsum('bl,mkl->bmk', betas, d['shapedirs'])
+    J0 = torch.einsum('bik,i->bk', v_shaped, d['J_regressor'][0])[:, None]
+    assert torch.allclose(v2, (v - J0) @ Q.transpose(1, 2) + J0, atol=5e-6)
+    assert torch.allclose(J2, (J - J0) @ Q.transpose(1, 2) + J0, atol=5e-6)
+    assert torch.allclose(J[:, 0], J0[:, 0], atol=2e-6)               # the root joint itself does not move
+
+
+def test_lbs_against_an_independent_float64_forward_kinematics():
+    """The vectorised restatement (oracle/head.py::lbs) against a per-vertex, per-joint float64 loop written from the
+    definition: G_j = G_parent(j) [R_j | J_j - J_parent(j)], v = sum_j w_vj G_j [R|t] applied to (v_posed - J_j)."""
+    d = {k: np.asarray(v, dtype=np.float64) for k, v in synthetic_smpl_data(0).items() if k != 'parents'}
+    parents = [int(p) for p in synthetic_smpl_data(0)['parents']]
+    betas = torch.randn(2, 10, generator=torch.Generator().manual_seed(4))
+    R = _random_rotmats(2 * 24, 5).reshape(2, 24, 3, 3)
+    dt = {k: torch.as_tensor(v).float() for k, v in d.items()}
+    v, J = lbs(betas, R, dt['v_template'], dt['shapedirs'], dt['posedirs'], dt['J_regressor'], parents, dt['lbs_weights'])
+    vidx = [0, 17, 1234, 3456, 6889]
+    for b in range(2):
+        be, Rb = betas[b].double().numpy(), R[b].double().numpy()
+        v_shaped = d['v_template'] + d['shapedirs'] @ be                      # (6890,3)
+        Jr = d['J_regressor'] @ v_shaped                                       # (24,3)
+        pf = (Rb[1:] - np.eye(3)).reshape(-1)
+        v_posed = v_shaped + (pf @ d['posedirs']).reshape(-1, 3)
+        Grot, Gt = [None] * 24, [None] * 24                                    # world rotation / translation of each joint
+        for j in range(24):
+            if j == 0:
+                Grot[j], Gt[j] = Rb[0], Jr[0]
+            else:
+                pa = parents[j]
+                Grot[j] = Grot[pa] @ Rb[j]
+                Gt[j] = Grot[pa] @ (Jr[j] - Jr[pa]) + Gt[pa]
+        for k in range(24):
+            assert np.allclose(J[b, k].numpy(), Gt[k], atol=5e-6)
+        for vi in vidx:
+            out = np.zeros(3)
+            for j in range(24):
+                out += d['lbs_weights'][vi, j] * (Grot[j] @ (v_posed[vi] - Jr[j]) + Gt[j])
+            assert np.allclose(v[b, vi].numpy(), out, atol=5e-6), (b, vi)
+
+
 def test_projection_optical_axis_and_k22():
     B = 4
     K = torch.zeros(B, 3, 3); K[:, 0, 0] = K[:, 1, 1] = 1000.; K[:, 0, 2] = 960.; K[:, 1, 2] = 540.   # K[2,2]=0 as cam_params.py
