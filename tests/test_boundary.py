@@ -343,3 +343,37 @@ def test_inplace_parameter_updates_are_noticed():
     with torch.no_grad():
         t.layer1._modules['0'].conv1.weight.mul_(2.0)
     assert t._weights_changed()
+
+
+def test_dependent_launch_rule_holds_for_every_kernel():
+    """Source lint for the programmatic-dependent-launch rule (csrc/common.cuh): a kernel that is launched through
+    ``launch_dep`` may start before its stream predecessor has finished, so it must execute ``griddep_wait()`` before it
+    touches activations.  Every ``__global__`` kernel of the library that is NOT launched with ``<<<...>>>`` somewhere is
+    launched through ``launch_dep`` (directly or through a function-pointer alias) and has to contain the wait; and no
+    kernel may be launched both ways."""
+    csrc = os.path.join(ROOT, 'spec_b200', 'csrc')
+    text = {f: open(os.path.join(csrc, f)).read() for f in sorted(os.listdir(csrc)) if f.endswith(('.cu', '.cuh'))}
+    kernels = {}
+    for f, s in text.items():
+        for m in re.finditer(r'__global__\s+void\s+(?:__\w+__\s*\([^)]*\)\s*)*(\w+)\s*\(', s):
+            i = s.index('{', m.end())
+            depth, j = 0, i
+            while True:                                            # brace-match the kernel body
+                depth += {'{': 1, '}': -1}.get(s[j], 0)
+                j += 1
+                if depth == 0:
+                    break
+            kernels[m.group(1)] = (f, s[i:j])
+    assert len(kernels) > 25, sorted(kernels)
+    allsrc = '\n'.join(text.values())
+    plain = {k for k in kernels if re.search(r'\b' + k + r'\b\s*(<[^;()]*?>)?\s*<<<', allsrc)}
+    dep = {k for k in kernels if re.search(r'launch_dep\(\s*' + k + r'\b', allsrc)}
+    aliased = {k for k in kernels if re.search(r'auto\s+\w+\s*=\s*' + k + r'\b', allsrc)}     # k0 = conv_tcp_kernel<...>; launched via launch_dep(k0, ...)
+    assert dep and aliased
+    assert not (plain & (dep | aliased)), sorted(plain & (dep | aliased))
+    assert (dep | aliased | plain) == set(kernels), sorted(set(kernels) - (dep | aliased | plain))
+    for k in sorted(dep | aliased):
+        f, body = kernels[k]
+        assert 'griddep_wait()' in body, f'{f}: {k} is launched with programmatic dependent launch but never calls griddep_wait()'
+        first_ret = body.find('return;')
+        assert first_ret < 0 or body.find('griddep_wait()') < first_ret, f'{f}: {k} can return before griddep_wait()'
